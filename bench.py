@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the MaxStyle layer hot path (BASELINE.json metric: fwd+bwd samples/s and
+achieved HBM GB/s on B200 vs the host CPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic feature maps: forward,
+backward (dX + the three parameter gradients) and the optimiser step fused into the backward
+epilogue.  Workload = BASELINE config 1 shape (the FCN_64 decoder's layer-4 activation of
+config 2): fp32 NCHW, 20 x 64 x 224 x 224 per GPU, x ~ N(0,1)*1.5+0.25, dy ~ N(0,1).  With N > 1
+the batch shards data-parallel (20 per GPU, weak scaling) and mixing partners come from the
+global batch through the one all-gather of the [N,2C] (mu|sig) tables.
+
+Prints ONE JSON line (rank 0).  `value` times the device-resident path with CUDA events,
+`e2e` the same step through the public module API from pinned HOST buffers (H2D of x and dy,
+D2H of y, dX and the parameter gradients inside the timed region).  `roofline` is the dominant
+kernel (the backward sweep) against the measured HBM copy peak of MEASURED_PEAKS.json;
+`cpu_baseline` is the reference's op chain (oracle/torch_port.py) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "maxstyle_layer_fwd_bwd_step_samples_per_sec"
+UNIT = "samples/s"
+SHAPE = dict(N=20, C=64, H=224, W=224)            # per GPU
+HBM_FALLBACK_GBS = 6650.0                         # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def workload_config(n_gpus: int) -> dict:
+    s = SHAPE
+    return {
+        "workload": f"MaxStyle layer fwd+bwd+fused Adam step, fp32 NCHW {s['N']}x{s['C']}x{s['H']}x{s['W']} per GPU "
+                    "(BASELINE config-1 shape = FCN_64 layer-4 activation of config 2), all params learnable, p=1",
+        "per_gpu_batch": s["N"], "global_batch": s["N"] * n_gpus, "channels": s["C"], "height": s["H"], "width": s["W"],
+        "layout": "NCHW", "parallelism": f"dp{n_gpus}" + ("+allgather(mu,sig)" if n_gpus > 1 else ""),
+        "l2_policy": "working set 1.03 GB per GPU (x, y, dy, dx of 257 MB each) >> 126 MB L2; no explicit flush",
+    }
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("bwd_nchw_kernel", {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------
+# clocks: nvidia-smi sampled DURING the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=self.out, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation of the path (oracle port) on the host cores
+# --------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle.torch_port import time_cpu_baseline
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    s = SHAPE
+    # each "step" is the full per-GPU batch of the workload; bounded: warmup W (<=2), K steps capped by a time budget
+    budget = 60.0
+    res = time_cpu_baseline(s["N"], s["C"], s["H"], s["W"], budget_s=budget, min_iters=max(1, min(args.steps, 5)),
+                            warmup=max(1, min(args.warmup, 2)), threads=threads)
+    value = res["samples_per_s"]
+    sample = (f"{res['iters']} timed steps (best-of) of the full per-GPU batch {s['N']}x{s['C']}x{s['H']}x{s['W']} fp32, "
+              f"fwd+bwd+torch.optim.Adam step, after {max(1, min(args.warmup, 2))} warm-up")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": res["iters"],
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": res["seconds_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference's eager ATen op chain + autograd + Adam (oracle/torch_port.py, validated against "
+                "reference-generated goldens) on the host cores; the Python reference itself cannot travel to this box",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from maxstyle_b200 import MaxStyle, FusedStyleOptimizer, GlobalBatchMaxStyle
+    from maxstyle_b200 import functional as F
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    s = SHAPE
+    n, c, h, w = s["N"], s["C"], s["H"], s["W"]
+    E = n * c * h * w
+    torch.manual_seed(1234)                                  # identical on every rank: global-batch state contract
+    layer = (GlobalBatchMaxStyle(n, c, p=1.0) if world > 1 else MaxStyle(n, c, p=1.0))
+    opt = FusedStyleOptimizer([layer], lr=0.1, mode="adam")
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)
+    x = (torch.randn(n, c, h, w, device=dev, generator=gen) * 1.5 + 0.25).requires_grad_(True)
+    dy = torch.randn(n, c, h, w, device=dev, generator=gen)
+
+    def step():
+        y = layer(x)
+        x.grad = None
+        y.backward(dy)
+        opt.step()
+        return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: exactly K steps, CUDA events on the launching (current) stream ------
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = F.launches.kernels
+    barrier()
+    e_begin.record()
+    for i in range(K):
+        ev[i][0].record()
+        y = layer(x)
+        ev[i][1].record()
+        x.grad = None
+        y.backward(dy)
+        ev[i][2].record()
+        opt.step()
+    e_end.record()
+    barrier()
+    launches = F.launches.kernels - launches0
+    total_ms = e_begin.elapsed_time(e_end)
+    fwd_ms = statistics.fmean(ev[i][0].elapsed_time(ev[i][1]) for i in range(K))
+    bwd_ms = statistics.fmean(ev[i][1].elapsed_time(ev[i][2]) for i in range(K))
+    # keep the same load running (untimed) long enough for nvidia-smi's 100 ms sampling to see it
+    t_hold = time.perf_counter()
+    while rank == 0 and world == 1 and time.perf_counter() - t_hold < 1.5:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+    if world > 1:
+        for _ in range(200):
+            step()
+        barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([total_ms, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, fwd_ms, bwd_ms = (float(v) for v in t.tolist())
+    ms_per_step = total_ms / K
+    value = world * n * K / (total_ms * 1e-3)
+
+    # ---- e2e: same step through the public module API from pinned host buffers --------------
+    e2e = None
+    if not args.no_e2e:
+        hx = torch.empty(n, c, h, w, dtype=torch.float32, pin_memory=True).copy_(x.detach())
+        hdy = torch.empty(n, c, h, w, dtype=torch.float32, pin_memory=True).copy_(dy)
+        hy = torch.empty(n, c, h, w, dtype=torch.float32, pin_memory=True)
+        hdx = torch.empty(n, c, h, w, dtype=torch.float32, pin_memory=True)
+        hp = torch.empty(2 * n * c + n, dtype=torch.float32, pin_memory=True)
+        dxin = torch.empty_like(x.detach()).requires_grad_(True)
+        ddy = torch.empty_like(dy)
+
+        def e2e_step():
+            with torch.no_grad():
+                dxin.copy_(hx, non_blocking=True)            # H2D x
+            ddy.copy_(hdy, non_blocking=True)                # H2D dy
+            yy = layer(dxin)
+            dxin.grad = None
+            yy.backward(ddy)
+            opt.step()
+            hy.copy_(yy.detach(), non_blocking=True)         # D2H y
+            hdx.copy_(dxin.grad, non_blocking=True)          # D2H dX
+            hp.copy_(torch.cat([layer.gamma_noise.detach().flatten(), layer.beta_noise.detach().flatten(),
+                                layer.lmda.detach().flatten()]), non_blocking=True)   # D2H updated style parameters
+            torch.cuda.current_stream().synchronize()        # the caller reads the result on the host
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ke = max(1, args.e2e_steps)
+        for _ in range(ke):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        e2e = {"value": world * n * ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * E * 4,
+               "d2h_bytes_per_step": 2 * E * 4 + (2 * n * c + n) * 4, "steps": ke, "ms_per_step": e2e_s / ke * 1e3,
+               "note": "pinned host x,dy -> H2D -> layer fwd/bwd/fused step -> D2H y,dX,params; PCIe-bound"}
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        bwd_bytes = 3 * E * 4                                  # read dy, read x, write dX
+        step_bytes = 5 * E * 4                                 # + forward: read x, write y
+        achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "roofline": {"bound": "hbm", "kernel": "bwd_nchw_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_ms": bwd_ms},
+            "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved_GBps": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                              "frac_of_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                              "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                              "fwd_GBps_algorithmic": 2 * E * 4 / (fwd_ms * 1e-3) / 1e9},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle.torch_port import time_cpu_baseline
+            torch.set_num_threads(os.cpu_count() or 1)
+            res = time_cpu_baseline(n, c, h, w, budget_s=12.0, min_iters=3, warmup=1, threads=os.cpu_count() or 1)
+            line["cpu_baseline"] = {
+                "value": res["samples_per_s"], "unit": UNIT, "cores": res["threads"], "kind": "port",
+                "sample": f"{res['iters']} timed steps (best-of) of the full batch {n}x{c}x{h}x{w} fp32 fwd+bwd+Adam step "
+                          "of the reference's ATen op chain (oracle/torch_port.py), 1 warm-up",
+                "ms_per_step": res["seconds_per_step"] * 1e3}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

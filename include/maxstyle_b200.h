@@ -1,0 +1,150 @@
+/*
+ * maxstyle_b200.h -- C ABI of the B200-native MaxStyle feature-style layer.
+ *
+ * This is the drop-in boundary for ONE hot path of cherise215/MaxStyle: the layer in
+ * src/advanced/maxstyle.py (forward :140-189, the backward autograd derives from it, and
+ * the optimiser step its caller applies at
+ * src/models/advanced_triplet_recon_segmentation_model.py:537,562).  The reference has no
+ * native code or FFI for this path; these entry points are what a
+ * binding for it would call, and maxstyle_b200/_lib.py binds them with ctypes.
+ *
+ * Conventions
+ *  - Plain C: pointers + sizes, no torch / C++ types.  The caller owns every buffer; the
+ *    library never allocates or frees device memory and keeps no mutable global state.
+ *  - All work is enqueued on the caller's `stream`; no host synchronisation, no default
+ *    stream use, graph-capturable.  Re-entrant and thread-safe (autograd calls the backward
+ *    from its own thread).  The caller selects the device (cudaSetDevice / device guard).
+ *  - Return value: MAXSTYLE_OK or an error code (maxstyle_strerror()).  No exceptions, no abort.
+ *  - `workspace` must hold maxstyle_workspace_bytes() bytes, be 256-byte aligned and be
+ *    ZERO-FILLED ONCE by the caller before its first use; every call leaves the counters in
+ *    it zeroed again, so it can be reused by later calls on the same stream.
+ *  - Style tables are fp32 and row-major [rows, C]: mu / sig / scale / shift, gamma_noise /
+ *    beta_noise ([N,C,1,1] in the reference) ; lmda is [N] ([N,1,1,1] in the reference);
+ *    gamma_std / beta_std are [C] ([1,C,1,1] in the reference); perm is int64 [N_global].
+ *  - Global-batch (multi-GPU) extension: a rank holds rows [row_offset, row_offset+N) of a
+ *    global batch of N_global samples; `mu_all`/`sig_all` are [N_global, C] and perm indexes
+ *    the global batch.  Single GPU: N_global == N, row_offset == 0.
+ *  - `table_ld` is the number of floats between consecutive rows of mu_all / sig_all (>= C).
+ *    ld == C for two separate [N_global, C] arrays; ld == 2C with sig_all == mu_all + C for one
+ *    interleaved [N_global, 2C] buffer (the shape one all-gather of per-rank blocks produces).
+ */
+#ifndef MAXSTYLE_B200_H_
+#define MAXSTYLE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* opaque: a cudaStream_t passed as void* so that the header needs no CUDA include */
+typedef void* maxstyle_stream_t;
+
+enum {
+    MAXSTYLE_OK = 0,
+    MAXSTYLE_ERR_BAD_ARG = 1,      /* null pointer / non-positive size / inconsistent rows   */
+    MAXSTYLE_ERR_UNSUPPORTED = 2,  /* dtype / layout / shape this build has no kernel for    */
+    MAXSTYLE_ERR_WORKSPACE = 3,    /* workspace missing, too small or misaligned             */
+    MAXSTYLE_ERR_CUDA = 4,         /* cudaGetLastError() after a launch was not cudaSuccess  */
+    MAXSTYLE_ERR_NO_DEVICE = 5     /* no sm_100 device / wrong architecture                  */
+};
+
+enum { MAXSTYLE_F32 = 0, MAXSTYLE_BF16 = 1 };           /* element type of x / y / dy / dx      */
+enum { MAXSTYLE_NCHW = 0, MAXSTYLE_NHWC = 1 };          /* memory layout of x / y / dy / dx     */
+
+/* flags */
+enum {
+    MAXSTYLE_MIX_STYLE = 1,         /* maxstyle.py:172-176 (else :177-179)                     */
+    MAXSTYLE_NO_NOISE = 2,          /* maxstyle.py:181-182 (else :183-185)                     */
+    MAXSTYLE_COMPUTE_BATCH_STD = 4  /* first forward: fill gamma_std/beta_std (maxstyle.py:165-168);
+                                       otherwise they are inputs (the reference's cached values) */
+};
+
+/* optimiser step fused into the backward epilogue (north_star item 4) */
+enum {
+    MAXSTYLE_STEP_NONE = 0,
+    MAXSTYLE_STEP_ADAM = 1,  /* torch.optim.Adam semantics, the reference's choice (model:537)  */
+    MAXSTYLE_STEP_SIGN = 2   /* p -= lr*sign(g) (or += with maximize): sign-gradient step       */
+};
+
+typedef struct maxstyle_step {
+    int32_t mode;            /* MAXSTYLE_STEP_*                                                   */
+    int32_t maximize;        /* 0: descend the gradient handed to the backward (the reference
+                                backpropagates -CE, model:555);  1: ascend it                    */
+    double lr, beta1, beta2, eps; /* doubles: bias corrections are computed like torch does, in fp64 */
+    int32_t t;               /* 1-based step number for Adam's bias correction; ignored when
+                                step_dev != NULL                                                  */
+    int32_t update_noise;    /* gamma_noise / beta_noise are learnable (noise_learnable)          */
+    int32_t update_mix;      /* lmda is learnable (mix_learnable)                                 */
+    int32_t reserved;
+    int32_t* step_dev;       /* optional device counter: the kernel uses *step_dev+1 as t and
+                                increments it once per call (CUDA-graph replay friendly)         */
+    float* gamma_noise;      /* [N,C] updated in place                                            */
+    float* beta_noise;       /* [N,C]                                                             */
+    float* lmda;             /* [N]                                                               */
+    float* gamma_m; float* gamma_v;   /* Adam exp_avg / exp_avg_sq, same shapes as the parameter */
+    float* beta_m;  float* beta_v;
+    float* lmda_m;  float* lmda_v;
+} maxstyle_step_t;
+
+/* Library / build identification, e.g. "maxstyle_b200 0.1 sm_100a". */
+const char* maxstyle_version(void);
+const char* maxstyle_strerror(int code);
+
+/* Bytes of scratch the calls below need for this problem (counters + per-tile partials). */
+size_t maxstyle_workspace_bytes(int N, int C, int H, int W, int dtype, int layout);
+
+/* Kernel 1 -- instance statistics (replaces x.mean / x.var / sqrt, maxstyle.py:157-159).
+ * One pass over x; per-(n,c) plane mean and sqrt(unbiased var + eps) by Welford/Chan
+ * merging.  Writes rows [row_offset, row_offset+N) of mu_all / sig_all. */
+int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, int row_offset,
+                   int N, int C, int H, int W, int dtype, int layout, float eps,
+                   void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
+
+/* Table step (replaces maxstyle.py:165-185 on the [N,C] tables): optional batch std,
+ * clamp(lmda), partner gather through perm, lerp, noise perturbation.  Produces for the
+ * local rows  scale = A/sig  and  shift = B  with  A = sig_mix + gamma_noise*gamma_std,
+ * B = mu_mix + beta_noise*beta_std, so that  y = (x - mu)*scale + shift. */
+int maxstyle_tables(const float* mu_all, const float* sig_all, int table_ld, int N_global, int row_offset,
+                    int N, int C,
+                    const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
+                    float* gamma_std, float* beta_std, int flags,
+                    float* scale, float* shift, maxstyle_stream_t stream);
+
+/* Kernel 2 -- apply (replaces the normalise + affine chain, maxstyle.py:161,181-185). */
+int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, int row_offset, const float* scale,
+                   const float* shift, int N, int C, int H, int W, int dtype, int layout,
+                   maxstyle_stream_t stream);
+
+/* Whole forward on one GPU (N_global == N): stats -> tables -> apply, one call.
+ * Replaces MaxStyle.forward's active path (maxstyle.py:157-185). */
+int maxstyle_fwd(const void* x, void* y, float* mu, float* sig,
+                 const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
+                 float* gamma_std, float* beta_std, float* scale, float* shift,
+                 int N, int C, int H, int W, int dtype, int layout, int flags, float eps,
+                 void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
+
+/* Kernel 3 -- backward (replaces the autograd graph of maxstyle.py:157-185).
+ * One sweep over dy and x:  dx = dy*scale (skipped when dx == NULL),  dA = sum dy*(x-mu)/sig,
+ * dB = sum dy;  epilogue per sample:  d_gamma = dA*gamma_std,  d_beta = dB*beta_std,
+ * d_lmda = [0<=lmda<=1] * sum_c (dA*(sig[perm]-sig) + dB*(mu[perm]-mu)),  then the optional
+ * fused optimiser step.  d_gamma / d_beta / d_lmda may each be NULL (gradient not wanted). */
+int maxstyle_bwd(const void* dy, const void* x, void* dx,
+                 const float* mu_all, const float* sig_all, int table_ld, int N_global, int row_offset,
+                 const float* scale, const int64_t* perm, const float* lmda,
+                 const float* gamma_std, const float* beta_std, int flags,
+                 float* d_gamma, float* d_beta, float* d_lmda,
+                 const maxstyle_step_t* step,
+                 int N, int C, int H, int W, int dtype, int layout,
+                 void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
+
+/* Stand-alone optimiser step on the three parameter tensors (same arithmetic as the fused
+ * epilogue; used when the gradients arrive through autograd's .grad instead). */
+int maxstyle_step(const float* d_gamma, const float* d_beta, const float* d_lmda,
+                  const maxstyle_step_t* step, int N, int C, maxstyle_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAXSTYLE_B200_H_ */

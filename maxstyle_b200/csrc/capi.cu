@@ -1,0 +1,263 @@
+// extern "C" boundary of libmaxstyle_b200.so -- see include/maxstyle_b200.h for the contract.
+#include "../../include/maxstyle_b200.h"
+#include "kernels_nchw.cuh"
+#include "tables.cuh"
+
+#include <cuda_runtime.h>
+
+namespace {
+
+using namespace ms;
+
+int sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return sms;
+}
+
+// largest power of two <= 32 dividing all the given addresses (nullptr entries are ignored)
+inline int common_align(const void* a, const void* b = nullptr, const void* c = nullptr) {
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c);
+    int al = 32;
+    while (al > 1 && (bits & (uintptr_t)(al - 1))) al >>= 1;
+    return al;
+}
+
+inline int check_launch() { return cudaGetLastError() == cudaSuccess ? MAXSTYLE_OK : MAXSTYLE_ERR_CUDA; }
+
+int check_shape(int N, int C, int H, int W, int dtype, int layout) {
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return MAXSTYLE_ERR_BAD_ARG;
+    if ((int64_t)H * W < 2) return MAXSTYLE_ERR_BAD_ARG;          // unbiased variance needs M >= 2
+    if (dtype != MAXSTYLE_F32 && dtype != MAXSTYLE_BF16) return MAXSTYLE_ERR_UNSUPPORTED;
+    if (layout != MAXSTYLE_NCHW) return MAXSTYLE_ERR_UNSUPPORTED;
+    return MAXSTYLE_OK;
+}
+
+int check_workspace(const void* ws, size_t bytes, const Workspace& w) {
+    if (ws == nullptr || bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 255u)) return MAXSTYLE_ERR_WORKSPACE;
+    return MAXSTYLE_OK;
+}
+
+ItemGeom geom_of(const Plan& p, int64_t M) {
+    ItemGeom g;
+    g.M = M; g.nvec = p.nvec; g.chunk = p.chunk; g.items = p.items; g.splits = p.splits;
+    return g;
+}
+
+int grid_for(const Plan& p, int sms) {
+    const int per_block = kThreads / p.group;
+    int64_t blocks = (p.items + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)sms * kBlocksPerSM;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+// Vector accesses a thread keeps in flight per tensor: sized so the fp32 copies of the loaded
+// values fit a 32-register budget (the kernels run 4 CTAs x 256 threads per SM, 64 regs/thread).
+template <int VEC, int TENSORS> constexpr int vpt_for() {
+    constexpr int v = 32 / (VEC * TENSORS);
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+}
+
+// ---- dispatch on (dtype, vector width, group size) ------------------------------------------
+template <typename T, int VEC, int G>
+void launch_stats(const void* x, float* mu, float* sig, TableRef tr, char* ws, const Workspace& w, const Plan& p, int64_t M,
+                  float eps, int grid, cudaStream_t s) {
+    stats_nchw_kernel<T, VEC, G, vpt_for<VEC, 1>(), Hint::kDefault><<<grid, kThreads, 0, s>>>(
+        static_cast<const T*>(x), mu, sig, tr, reinterpret_cast<float4*>(ws + w.partials),
+        reinterpret_cast<int*>(ws + w.plane_counters), geom_of(p, M), eps);
+}
+
+template <typename T, int VEC, int G>
+void launch_apply(const void* x, void* y, const float* mu, TableRef tr, const float* scale, const float* shift, const Plan& p,
+                  int64_t M, int grid, cudaStream_t s) {
+    apply_nchw_kernel<T, VEC, G, vpt_for<VEC, 1>()><<<grid, kThreads, 0, s>>>(static_cast<const T*>(x), static_cast<T*>(y), mu, tr,
+                                                                              scale, shift, geom_of(p, M));
+}
+
+template <typename T, int VEC, int G>
+void launch_bwd(const void* dy, const void* x, void* dx, char* ws, const Workspace& w, const Plan& p, int64_t M,
+                const BwdTables& tb, const StepArgs& st, int grid, cudaStream_t s) {
+    float4* partials = reinterpret_cast<float4*>(ws + w.partials);
+    int* counters = reinterpret_cast<int*>(ws + w.sample_counters);
+    int* done = reinterpret_cast<int*>(ws + w.done_counter);
+    if (dx)
+        bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), true><<<grid, kThreads, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x),
+                                                                         static_cast<T*>(dx), partials, counters, done,
+                                                                         geom_of(p, M), tb, st);
+    else
+        bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), false><<<grid, kThreads, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x),
+                                                                          nullptr, partials, counters, done, geom_of(p, M),
+                                                                          tb, st);
+}
+
+#define MS_DISPATCH_G(FN, T, V, plan, ...)                                                         \
+    do {                                                                                           \
+        if ((plan).group == 32) FN<T, V, 32>(__VA_ARGS__); else FN<T, V, 256>(__VA_ARGS__);        \
+    } while (0)
+
+#define MS_DISPATCH(FN, dtype, plan, ...)                                                          \
+    do {                                                                                           \
+        if ((dtype) == MAXSTYLE_F32) {                                                             \
+            if ((plan).vec == 8) MS_DISPATCH_G(FN, float, 8, plan, __VA_ARGS__);                   \
+            else if ((plan).vec == 4) MS_DISPATCH_G(FN, float, 4, plan, __VA_ARGS__);              \
+            else MS_DISPATCH_G(FN, float, 1, plan, __VA_ARGS__);                                   \
+        } else {                                                                                   \
+            if ((plan).vec == 16) MS_DISPATCH_G(FN, __nv_bfloat16, 16, plan, __VA_ARGS__);         \
+            else if ((plan).vec == 8) MS_DISPATCH_G(FN, __nv_bfloat16, 8, plan, __VA_ARGS__);      \
+            else MS_DISPATCH_G(FN, __nv_bfloat16, 1, plan, __VA_ARGS__);                           \
+        }                                                                                          \
+    } while (0)
+
+StepArgs to_step_args(const maxstyle_step_t* s) {
+    StepArgs a{};
+    if (s == nullptr) return a;
+    a.mode = s->mode; a.maximize = s->maximize; a.update_noise = s->update_noise; a.update_mix = s->update_mix;
+    a.lr = s->lr; a.beta1 = s->beta1; a.beta2 = s->beta2; a.eps = s->eps; a.t = s->t; a.step_dev = s->step_dev;
+    a.gamma_noise = s->gamma_noise; a.beta_noise = s->beta_noise; a.lmda = s->lmda;
+    a.gamma_m = s->gamma_m; a.gamma_v = s->gamma_v; a.beta_m = s->beta_m; a.beta_v = s->beta_v;
+    a.lmda_m = s->lmda_m; a.lmda_v = s->lmda_v;
+    return a;
+}
+
+int check_step(const maxstyle_step_t* s) {
+    if (s == nullptr || s->mode == MAXSTYLE_STEP_NONE) return MAXSTYLE_OK;
+    if (s->mode != MAXSTYLE_STEP_ADAM && s->mode != MAXSTYLE_STEP_SIGN) return MAXSTYLE_ERR_BAD_ARG;
+    const bool adam = s->mode == MAXSTYLE_STEP_ADAM;
+    if (s->update_noise) {
+        if (!s->gamma_noise || !s->beta_noise) return MAXSTYLE_ERR_BAD_ARG;
+        if (adam && (!s->gamma_m || !s->gamma_v || !s->beta_m || !s->beta_v)) return MAXSTYLE_ERR_BAD_ARG;
+    }
+    if (s->update_mix) {
+        if (!s->lmda) return MAXSTYLE_ERR_BAD_ARG;
+        if (adam && (!s->lmda_m || !s->lmda_v)) return MAXSTYLE_ERR_BAD_ARG;
+    }
+    if (adam && s->step_dev == nullptr && s->t < 1) return MAXSTYLE_ERR_BAD_ARG;
+    return MAXSTYLE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* maxstyle_version(void) { return "maxstyle_b200 0.1 (sm_100a)"; }
+
+const char* maxstyle_strerror(int code) {
+    switch (code) {
+        case MAXSTYLE_OK: return "ok";
+        case MAXSTYLE_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size, H*W < 2, or inconsistent rows)";
+        case MAXSTYLE_ERR_UNSUPPORTED: return "unsupported dtype / layout / shape";
+        case MAXSTYLE_ERR_WORKSPACE: return "workspace missing, too small or not 256-byte aligned";
+        case MAXSTYLE_ERR_CUDA: return "CUDA launch error";
+        case MAXSTYLE_ERR_NO_DEVICE: return "no usable CUDA device";
+        default: return "unknown error code";
+    }
+}
+
+size_t maxstyle_workspace_bytes(int N, int C, int H, int W, int dtype, int layout) {
+    if (check_shape(N, C, H, W, dtype, layout) != MAXSTYLE_OK) return 0;
+    return workspace_layout(N, C, (int64_t)H * W, dtype).total;
+}
+
+int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, int row_offset, int N, int C, int H, int W,
+                   int dtype, int layout, float eps, void* workspace, size_t workspace_bytes, maxstyle_stream_t stream) {
+    int rc = check_shape(N, C, H, W, dtype, layout);
+    if (rc) return rc;
+    if (!x || !mu_all || !sig_all || row_offset < 0 || table_ld < C) return MAXSTYLE_ERR_BAD_ARG;
+    const int64_t M = (int64_t)H * W;
+    const Workspace w = workspace_layout(N, C, M, dtype);
+    if ((rc = check_workspace(workspace, workspace_bytes, w))) return rc;
+    const int sms = sm_count();
+    if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+    const Plan p = make_plan(N, C, M, dtype, common_align(x));
+    const TableRef tr{C, table_ld, row_offset};
+    MS_DISPATCH(launch_stats, dtype, p, x, mu_all, sig_all, tr, static_cast<char*>(workspace), w, p, M, eps, grid_for(p, sms),
+                static_cast<cudaStream_t>(stream));
+    return check_launch();
+}
+
+int maxstyle_tables(const float* mu_all, const float* sig_all, int table_ld, int N_global, int row_offset, int N, int C,
+                    const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
+                    float* gamma_std, float* beta_std, int flags, float* scale, float* shift, maxstyle_stream_t stream) {
+    if (!mu_all || !sig_all || !scale || !shift) return MAXSTYLE_ERR_BAD_ARG;
+    if (N <= 0 || C <= 0 || N_global < N || row_offset < 0 || row_offset + N > N_global || table_ld < C)
+        return MAXSTYLE_ERR_BAD_ARG;
+    if ((flags & MAXSTYLE_MIX_STYLE) && (!perm || !lmda)) return MAXSTYLE_ERR_BAD_ARG;
+    if (!(flags & MAXSTYLE_NO_NOISE) && (!gamma_noise || !beta_noise || !gamma_std || !beta_std)) return MAXSTYLE_ERR_BAD_ARG;
+    tables_kernel<<<C, kTableThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        mu_all, sig_all, table_ld, N_global, row_offset, N, C, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, flags,
+        scale, shift);
+    return check_launch();
+}
+
+int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, int row_offset, const float* scale,
+                   const float* shift, int N, int C, int H, int W, int dtype, int layout, maxstyle_stream_t stream) {
+    int rc = check_shape(N, C, H, W, dtype, layout);
+    if (rc) return rc;
+    if (!x || !y || !mu_all || !scale || !shift || row_offset < 0 || table_ld < C) return MAXSTYLE_ERR_BAD_ARG;
+    const int sms = sm_count();
+    if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+    const int64_t M = (int64_t)H * W;
+    const Plan p = make_plan(N, C, M, dtype, common_align(x, y));
+    const TableRef tr{C, table_ld, row_offset};
+    MS_DISPATCH(launch_apply, dtype, p, x, y, mu_all, tr, scale, shift, p, M, grid_for(p, sms),
+                static_cast<cudaStream_t>(stream));
+    return check_launch();
+}
+
+int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* perm, const float* lmda,
+                 const float* gamma_noise, const float* beta_noise, float* gamma_std, float* beta_std, float* scale,
+                 float* shift, int N, int C, int H, int W, int dtype, int layout, int flags, float eps, void* workspace,
+                 size_t workspace_bytes, maxstyle_stream_t stream) {
+    int rc = maxstyle_stats(x, mu, sig, C, 0, N, C, H, W, dtype, layout, eps, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    rc = maxstyle_tables(mu, sig, C, N, 0, N, C, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, flags, scale, shift,
+                         stream);
+    if (rc) return rc;
+    return maxstyle_apply(x, y, mu, C, 0, scale, shift, N, C, H, W, dtype, layout, stream);
+}
+
+int maxstyle_bwd(const void* dy, const void* x, void* dx, const float* mu_all, const float* sig_all, int table_ld, int N_global,
+                 int row_offset, const float* scale, const int64_t* perm, const float* lmda, const float* gamma_std,
+                 const float* beta_std, int flags, float* d_gamma, float* d_beta, float* d_lmda, const maxstyle_step_t* step,
+                 int N, int C, int H, int W, int dtype, int layout, void* workspace, size_t workspace_bytes,
+                 maxstyle_stream_t stream) {
+    int rc = check_shape(N, C, H, W, dtype, layout);
+    if (rc) return rc;
+    if (!dy || !x || !mu_all || !sig_all || !scale) return MAXSTYLE_ERR_BAD_ARG;
+    if (N_global < N || row_offset < 0 || row_offset + N > N_global || table_ld < C) return MAXSTYLE_ERR_BAD_ARG;
+    if ((flags & MAXSTYLE_MIX_STYLE) && (!perm || !lmda)) return MAXSTYLE_ERR_BAD_ARG;
+    if (!(flags & MAXSTYLE_NO_NOISE) && (!gamma_std || !beta_std)) return MAXSTYLE_ERR_BAD_ARG;
+    if ((rc = check_step(step))) return rc;
+    const int64_t M = (int64_t)H * W;
+    const Workspace w = workspace_layout(N, C, M, dtype);
+    if ((rc = check_workspace(workspace, workspace_bytes, w))) return rc;
+    const int sms = sm_count();
+    if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+    const Plan p = make_plan(N, C, M, dtype, common_align(dy, x, dx));
+    BwdTables tb;
+    tb.mu_all = mu_all; tb.sig_all = sig_all; tb.scale = scale; tb.perm = perm; tb.lmda = lmda;
+    tb.gamma_std = gamma_std; tb.beta_std = beta_std; tb.d_gamma = d_gamma; tb.d_beta = d_beta; tb.d_lmda = d_lmda;
+    tb.row_offset = row_offset; tb.N = N; tb.C = C; tb.flags = flags; tb.ld = table_ld;
+    const StepArgs st = to_step_args(step);
+    MS_DISPATCH(launch_bwd, dtype, p, dy, x, dx, static_cast<char*>(workspace), w, p, M, tb, st, grid_for(p, sms),
+                static_cast<cudaStream_t>(stream));
+    return check_launch();
+}
+
+int maxstyle_step(const float* d_gamma, const float* d_beta, const float* d_lmda, const maxstyle_step_t* step, int N, int C,
+                  maxstyle_stream_t stream) {
+    if (N <= 0 || C <= 0 || step == nullptr || step->mode == MAXSTYLE_STEP_NONE) return MAXSTYLE_ERR_BAD_ARG;
+    int rc = check_step(step);
+    if (rc) return rc;
+    const StepArgs st = to_step_args(step);
+    const int64_t total = (int64_t)N * C;
+    const int blocks = (int)((total + 255) / 256);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    step_kernel<<<blocks, 256, 0, s>>>(d_gamma, d_beta, d_lmda, N, C, st);
+    if (st.mode == MAXSTYLE_STEP_ADAM && st.step_dev) step_count_kernel<<<1, 1, 0, s>>>(st.step_dev);
+    return check_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+// Device-side building blocks shared by the MaxStyle kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace ms {
+
+constexpr int kThreads = 256;          // threads per CTA for every streaming kernel
+constexpr int kWarps = kThreads / 32;
+
+// ----------------------------------------------------------------------------------------
+// Vectorised global access.  sm_100 adds 256-bit global loads/stores (SASS LDG.E.256 /
+// STG.E.256) and lets them carry an L2 eviction priority (.L2::evict_first / evict_last), which
+// the 128-bit forms cannot.  Vec<T,VEC> moves VEC elements of T per instruction:
+//   32 bytes (8 x f32 / 16 x bf16)  -- the fast path, planes 32-byte aligned
+//   16 bytes (4 x f32 /  8 x bf16)  -- planes only 16-byte aligned
+//   1 element                       -- ragged / unaligned planes
+// and converts to/from fp32 registers.
+// ----------------------------------------------------------------------------------------
+enum class Hint {
+    kDefault,   // no L2 priority
+    kStream,    // last use of the line: evict-first in L2
+    kKeep       // a later phase re-reads it: evict-last in L2
+};
+
+struct Words8 { uint32_t w[8]; };
+struct Words4 { uint32_t w[4]; };
+
+template <Hint H> __device__ __forceinline__ Words8 ld256(const void* p) {
+    Words8 r;
+    if constexpr (H == Hint::kStream) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                       "=r"(r.w[7]) : "l"(p));
+    } else if constexpr (H == Hint::kKeep) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                       "=r"(r.w[7]) : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                       "=r"(r.w[7]) : "l"(p));
+    }
+    return r;
+}
+
+// streaming store: the line is not read again by this pass, evict-first in L2
+__device__ __forceinline__ void st256_stream(void* p, const Words8& r) {
+    asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 ::"r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7]),
+                   "l"(p) : "memory");
+}
+
+__device__ __forceinline__ Words4 ld128(const void* p) {
+    Words4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void st128_stream(void* p, const Words4& r) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]), "r"(r.w[3])
+                 : "memory");
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// words <-> fp32 registers
+template <typename T, int NW> struct Unpack;
+template <int NW> struct Unpack<float, NW> {
+    static __device__ __forceinline__ void to(const uint32_t (&w)[NW], float (&v)[NW]) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) v[i] = __uint_as_float(w[i]);
+    }
+    static __device__ __forceinline__ void from(const float (&v)[NW], uint32_t (&w)[NW]) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = __float_as_uint(v[i]);
+    }
+};
+template <int NW> struct Unpack<__nv_bfloat16, NW> {
+    static __device__ __forceinline__ void to(const uint32_t (&w)[NW], float (&v)[2 * NW]) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {           // bf16 -> fp32 is a 16-bit shift
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ void from(const float (&v)[2 * NW], uint32_t (&w)[NW]) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+};
+
+template <typename T, int VEC> struct Vec {
+    static constexpr int kBytes = VEC * (int)sizeof(T);
+    static_assert(kBytes == 32 || kBytes == 16 || VEC == 1, "unsupported vector width");
+    template <Hint H> static __device__ __forceinline__ void load(const T* p, float (&v)[VEC]) {
+        if constexpr (VEC == 1) {
+            v[0] = to_f32<T>(__ldg(p));
+        } else if constexpr (kBytes == 32) {
+            const Words8 r = ld256<H>(p);
+            Unpack<T, 8>::to(r.w, v);
+        } else {
+            const Words4 r = ld128(p);
+            Unpack<T, 4>::to(r.w, v);
+        }
+    }
+    static __device__ __forceinline__ void store(T* p, const float (&v)[VEC]) {
+        if constexpr (VEC == 1) {
+            *p = from_f32<T>(v[0]);
+        } else if constexpr (kBytes == 32) {
+            Words8 r;
+            Unpack<T, 8>::from(v, r.w);
+            st256_stream(p, r);
+        } else {
+            Words4 r;
+            Unpack<T, 4>::from(v, r.w);
+            st128_stream(p, r);
+        }
+    }
+};
+
+// ----------------------------------------------------------------------------------------
+// Running moments (count, mean, M2 = sum of squared deviations) and their pairwise merge
+// (Chan et al.), the parallel form of Welford's update.
+// ----------------------------------------------------------------------------------------
+struct Moments {
+    float n, mean, m2;
+};
+
+__device__ __forceinline__ Moments merge(const Moments a, const Moments b) {
+    const float n = a.n + b.n;
+    if (n == 0.f) return a;
+    const float w = b.n / n;                  // IEEE division: these merges are off the per-element path
+    const float d = b.mean - a.mean;
+    Moments r;
+    r.n = n;
+    r.mean = fmaf(d, w, a.mean);
+    r.m2 = a.m2 + b.m2 + d * d * a.n * w;
+    return r;
+}
+
+__device__ __forceinline__ Moments shfl_xor(const Moments m, int lane_mask) {
+    Moments r;
+    r.n = __shfl_xor_sync(0xffffffffu, m.n, lane_mask);
+    r.mean = __shfl_xor_sync(0xffffffffu, m.mean, lane_mask);
+    r.m2 = __shfl_xor_sync(0xffffffffu, m.m2, lane_mask);
+    return r;
+}
+
+__device__ __forceinline__ Moments warp_merge(Moments m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = merge(m, shfl_xor(m, o));
+    return m;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Group = the G threads that cooperate on one work item: a warp (G == 32) or the CTA (G == 256).
+// The result is valid in every thread of the group.  `scratch` is per-CTA shared memory.
+struct Scratch {
+    float a[kWarps], b[kWarps], c[kWarps];
+    int flag;
+};
+
+template <int G> __device__ __forceinline__ Moments group_merge(Moments m, Scratch& s) {
+    m = warp_merge(m);
+    if constexpr (G > 32) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        __syncthreads();                                  // scratch may still be read from the previous use
+        if (lane == 0) { s.a[warp] = m.n; s.b[warp] = m.mean; s.c[warp] = m.m2; }
+        __syncthreads();
+        Moments t;
+        t.n = lane < kWarps ? s.a[lane] : 0.f;
+        t.mean = lane < kWarps ? s.b[lane] : 0.f;
+        t.m2 = lane < kWarps ? s.c[lane] : 0.f;
+#pragma unroll
+        for (int o = kWarps / 2; o > 0; o >>= 1) t = merge(t, shfl_xor(t, o));
+        m.n = __shfl_sync(0xffffffffu, t.n, 0);
+        m.mean = __shfl_sync(0xffffffffu, t.mean, 0);
+        m.m2 = __shfl_sync(0xffffffffu, t.m2, 0);
+    }
+    return m;
+}
+
+template <int G> __device__ __forceinline__ void group_sum2(float& u, float& v, Scratch& s) {
+    u = warp_sum(u);
+    v = warp_sum(v);
+    if constexpr (G > 32) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        __syncthreads();
+        if (lane == 0) { s.a[warp] = u; s.b[warp] = v; }
+        __syncthreads();
+        float tu = lane < kWarps ? s.a[lane] : 0.f;
+        float tv = lane < kWarps ? s.b[lane] : 0.f;
+#pragma unroll
+        for (int o = kWarps / 2; o > 0; o >>= 1) {
+            tu += __shfl_xor_sync(0xffffffffu, tu, o);
+            tv += __shfl_xor_sync(0xffffffffu, tv, o);
+        }
+        u = __shfl_sync(0xffffffffu, tu, 0);
+        v = __shfl_sync(0xffffffffu, tv, 0);
+    }
+}
+
+template <int G> __device__ __forceinline__ void group_sync() {
+    if constexpr (G > 32) __syncthreads(); else __syncwarp();
+}
+
+// "Last arriver" ticket: every group bumps `counter` after publishing its partial result;
+// the group that observes `total-1` owns the merge.  The winner resets the counter so the
+// workspace is left zeroed for the next call (see include/maxstyle_b200.h).
+template <int G> __device__ __forceinline__ bool arrive_is_last(int* counter, int total, Scratch& s) {
+    const int lane_in_group = G > 32 ? threadIdx.x : (threadIdx.x & 31);
+    int last = 0;
+    if (lane_in_group == 0) {
+        __threadfence();                                   // release: partial is visible before the ticket
+        const int prev = atomicAdd(counter, 1);
+        last = (prev == total - 1);
+        if (last) { *counter = 0; __threadfence(); }       // acquire side + reset
+    }
+    if constexpr (G > 32) {
+        __syncthreads();
+        if (threadIdx.x == 0) s.flag = last;
+        __syncthreads();
+        last = s.flag;
+    } else {
+        last = __shfl_sync(0xffffffffu, last, 0);
+    }
+    return last != 0;
+}
+
+}  // namespace ms

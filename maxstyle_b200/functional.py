@@ -1,0 +1,247 @@
+"""Thin tensor-level wrappers over the C ABI plus the autograd Function of the layer.
+
+PyTorch is plumbing here: it owns the device buffers and the stream; every computation on the
+path is a kernel of libmaxstyle_b200.so.  Nothing in this module computes with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_DTYPES = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+
+class _LaunchCounter:
+    """Counts kernels of libmaxstyle_b200.so enqueued through this module (bench.py's gpu_launches)."""
+    kernels = 0
+
+
+launches = _LaunchCounter()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"maxstyle_b200: {what} is on {t.device}; this layer only runs as CUDA kernels on a B200 "
+                           "(there is no CPU path)")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"maxstyle_b200: unsupported dtype {t.dtype} (float32 and bfloat16 are implemented)")
+
+
+def workspace_bytes(n: int, c: int, h: int, w: int, dtype: int, layout: int = L.NCHW) -> int:
+    return int(L.get_lib().maxstyle_workspace_bytes(n, c, h, w, dtype, layout))
+
+
+def new_workspace(n: int, c: int, h: int, w: int, dtype: int, device, layout: int = L.NCHW) -> torch.Tensor:
+    """Zero-filled scratch (the library keeps it zeroed between calls)."""
+    nbytes = workspace_bytes(n, c, h, w, dtype, layout)
+    if nbytes == 0:
+        raise RuntimeError(f"maxstyle_b200: no kernel for shape {(n, c, h, w)} dtype {dtype} layout {layout}")
+    return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+
+@dataclass
+class StepConfig:
+    """Optimiser step fused into the backward epilogue (maxstyle_step_t)."""
+    mode: int = L.STEP_ADAM
+    lr: float = 0.1
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    maximize: bool = False
+
+
+class FusedStepState:
+    """Adam moments + device step counter for the three parameters of one layer."""
+
+    def __init__(self, cfg: StepConfig, gamma_noise, beta_noise, lmda, update_noise: bool, update_mix: bool):
+        self.cfg = cfg
+        self.update_noise, self.update_mix = bool(update_noise), bool(update_mix)
+        dev = lmda.device
+        z = lambda t: torch.zeros_like(t, memory_format=torch.contiguous_format)
+        self.gamma_m, self.gamma_v = z(gamma_noise), z(gamma_noise)
+        self.beta_m, self.beta_v = z(beta_noise), z(beta_noise)
+        self.lmda_m, self.lmda_v = z(lmda), z(lmda)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.keep_grads = False
+
+    def struct(self, gamma_noise, beta_noise, lmda) -> L.StepStruct:
+        c = self.cfg
+        return L.StepStruct(
+            mode=c.mode, maximize=int(c.maximize), lr=c.lr, beta1=c.beta1, beta2=c.beta2, eps=c.eps, t=0,
+            update_noise=int(self.update_noise), update_mix=int(self.update_mix), reserved=0,
+            step_dev=self.step_dev.data_ptr(),
+            gamma_noise=_ptr(gamma_noise), beta_noise=_ptr(beta_noise), lmda=_ptr(lmda),
+            gamma_m=_ptr(self.gamma_m), gamma_v=_ptr(self.gamma_v), beta_m=_ptr(self.beta_m), beta_v=_ptr(self.beta_v),
+            lmda_m=_ptr(self.lmda_m), lmda_v=_ptr(self.lmda_v))
+
+
+# --------------------------------------------------------------------------------------------
+# raw calls (used by the autograd Function, the distributed layer, tests and bench)
+# --------------------------------------------------------------------------------------------
+def table_ld(mu_all: torch.Tensor) -> int:
+    """Floats between consecutive rows of a style table (it may be a column slice of a wider buffer)."""
+    if mu_all.dim() != 2 or mu_all.stride(1) != 1:
+        raise RuntimeError("maxstyle_b200: style tables must be 2-d with unit stride along channels")
+    return int(mu_all.stride(0))
+
+
+def instance_stats(x: torch.Tensor, eps: float, workspace: torch.Tensor, mu_all=None, sig_all=None, row_offset: int = 0):
+    """Kernel 1.  Returns (mu_all, sig_all) with rows [row_offset, row_offset+N) filled."""
+    _require_cuda(x, "x")
+    n, c, h, w = x.shape
+    if mu_all is None:
+        mu_all = torch.empty(n, c, dtype=torch.float32, device=x.device)
+        sig_all = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    rc = L.get_lib().maxstyle_stats(x.data_ptr(), mu_all.data_ptr(), sig_all.data_ptr(), table_ld(mu_all), row_offset,
+                                    n, c, h, w, dtype_code(x), L.NCHW, eps, workspace.data_ptr(), workspace.numel(),
+                                    _stream())
+    L.check(rc, "maxstyle_stats")
+    launches.kernels += 1
+    return mu_all, sig_all
+
+
+def style_tables(mu_all, sig_all, row_offset: int, n_local: int, perm_dev, lmda, gamma_noise, beta_noise,
+                 gamma_std, beta_std, flags: int, scale=None, shift=None):
+    n_global, c = mu_all.shape
+    if scale is None:
+        scale = torch.empty(n_local, c, dtype=torch.float32, device=mu_all.device)
+        shift = torch.empty(n_local, c, dtype=torch.float32, device=mu_all.device)
+    rc = L.get_lib().maxstyle_tables(mu_all.data_ptr(), sig_all.data_ptr(), table_ld(mu_all), n_global, row_offset,
+                                     n_local, c, _ptr(perm_dev), _ptr(lmda), _ptr(gamma_noise), _ptr(beta_noise),
+                                     _ptr(gamma_std), _ptr(beta_std), flags, scale.data_ptr(), shift.data_ptr(), _stream())
+    L.check(rc, "maxstyle_tables")
+    launches.kernels += 1
+    return scale, shift
+
+
+def style_apply(x, mu_all, row_offset: int, scale, shift, out=None):
+    n, c, h, w = x.shape
+    y = torch.empty_like(x, memory_format=torch.contiguous_format) if out is None else out
+    rc = L.get_lib().maxstyle_apply(x.data_ptr(), y.data_ptr(), mu_all.data_ptr(), table_ld(mu_all), row_offset,
+                                    scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), L.NCHW, _stream())
+    L.check(rc, "maxstyle_apply")
+    launches.kernels += 1
+    return y
+
+
+def forward_raw(x, perm_dev, lmda, gamma_noise, beta_noise, gamma_std, beta_std, flags: int, eps: float, workspace,
+                out=None, tables=None):
+    """maxstyle_fwd: whole single-GPU forward.  Returns (y, mu, sig, scale, shift)."""
+    _require_cuda(x, "x")
+    n, c, h, w = x.shape
+    if tables is None:
+        tables = torch.empty(4, n, c, dtype=torch.float32, device=x.device)
+    mu, sig, scale, shift = tables[0], tables[1], tables[2], tables[3]
+    y = torch.empty_like(x, memory_format=torch.contiguous_format) if out is None else out
+    rc = L.get_lib().maxstyle_fwd(x.data_ptr(), y.data_ptr(), mu.data_ptr(), sig.data_ptr(), _ptr(perm_dev), _ptr(lmda),
+                                  _ptr(gamma_noise), _ptr(beta_noise), _ptr(gamma_std), _ptr(beta_std),
+                                  scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), L.NCHW, flags, eps,
+                                  workspace.data_ptr(), workspace.numel(), _stream())
+    L.check(rc, "maxstyle_fwd")
+    launches.kernels += 3            # stats + tables + apply
+    return y, mu, sig, scale, shift
+
+
+def backward_raw(dy, x, mu_all, sig_all, row_offset: int, scale, perm_dev, lmda, gamma_std, beta_std, flags: int,
+                 workspace, need_dx: bool = True, need_noise_grad: bool = True, need_mix_grad: bool = True,
+                 step: Optional[L.StepStruct] = None, dx_out=None, grads_out=None):
+    """maxstyle_bwd.  Returns (dx | None, d_gamma | None, d_beta | None, d_lmda | None)."""
+    _require_cuda(dy, "dy")
+    n, c, h, w = x.shape
+    dx = None
+    if need_dx:
+        dx = torch.empty_like(x, memory_format=torch.contiguous_format) if dx_out is None else dx_out
+    dg = db = dl = None
+    if grads_out is not None:
+        dg, db, dl = grads_out
+    else:
+        if need_noise_grad:
+            dg = torch.empty(n, c, dtype=torch.float32, device=x.device)
+            db = torch.empty(n, c, dtype=torch.float32, device=x.device)
+        if need_mix_grad:
+            dl = torch.empty(n, dtype=torch.float32, device=x.device)
+    rc = L.get_lib().maxstyle_bwd(dy.data_ptr(), x.data_ptr(), _ptr(dx), mu_all.data_ptr(), sig_all.data_ptr(),
+                                  table_ld(mu_all), mu_all.shape[0], row_offset, scale.data_ptr(), _ptr(perm_dev), _ptr(lmda),
+                                  _ptr(gamma_std), _ptr(beta_std), flags, _ptr(dg), _ptr(db), _ptr(dl),
+                                  C.byref(step) if step is not None else None,
+                                  n, c, h, w, dtype_code(x), L.NCHW, workspace.data_ptr(), workspace.numel(), _stream())
+    L.check(rc, "maxstyle_bwd")
+    launches.kernels += 1
+    return dx, dg, db, dl
+
+
+# --------------------------------------------------------------------------------------------
+# autograd glue
+# --------------------------------------------------------------------------------------------
+class MaxStyleFunction(torch.autograd.Function):
+    """y = MaxStyle(x; gamma_noise, beta_noise, lmda).  `layer` supplies the non-differentiable
+    state (perm, cached gamma_std/beta_std, flags, workspace, optional fused step)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma_noise, beta_noise, lmda, layer):
+        x = x.contiguous()
+        flags = layer._flags()
+        first = layer.gamma_std is None or layer.beta_std is None
+        if first:
+            gamma_std = torch.empty(1, layer.num_feature, 1, 1, dtype=torch.float32, device=x.device)
+            beta_std = torch.empty(1, layer.num_feature, 1, 1, dtype=torch.float32, device=x.device)
+            flags |= L.FLAG_COMPUTE_BATCH_STD
+        else:
+            gamma_std, beta_std = layer.gamma_std, layer.beta_std
+        ws = layer._workspace_for(x)
+        y, mu, sig, scale, shift = forward_raw(x, layer._perm_device(x.device), lmda, gamma_noise, beta_noise,
+                                               gamma_std, beta_std, flags, layer.eps, ws)
+        if first:                      # cached until reset(), like the reference (maxstyle.py:165-168)
+            layer.gamma_std, layer.beta_std = gamma_std, beta_std
+        ctx.layer = layer
+        ctx.flags = flags & ~L.FLAG_COMPUTE_BATCH_STD
+        ctx.tables = (mu, sig, scale, gamma_std, beta_std)
+        ctx.save_for_backward(x, lmda)
+        ctx.set_materialize_grads(False)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        if dy is None:
+            return None, None, None, None, None
+        x, lmda = ctx.saved_tensors
+        layer = ctx.layer
+        mu, sig, scale, gamma_std, beta_std = ctx.tables
+        need_dx, need_g, need_b, need_l = ctx.needs_input_grad[:4]
+        fused = layer._fused_step
+        step = fused.struct(layer.gamma_noise, layer.beta_noise, layer.lmda) if fused is not None else None
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        with torch.cuda.device(x.device):
+            dx, dg, db, dl = backward_raw(dy, x, mu, sig, 0, scale, layer._perm_device(x.device), lmda, gamma_std,
+                                          beta_std, ctx.flags, layer._workspace_for(x), need_dx=need_dx,
+                                          need_noise_grad=(need_g or need_b) and (fused is None or fused.keep_grads),
+                                          need_mix_grad=need_l and (fused is None or fused.keep_grads), step=step)
+        n, c = x.shape[0], x.shape[1]
+        if fused is not None and not fused.keep_grads:
+            return dx, None, None, None, None
+        return (dx,
+                dg.view(n, c, 1, 1) if (need_g and dg is not None) else None,
+                db.view(n, c, 1, 1) if (need_b and db is not None) else None,
+                dl.view(n, 1, 1, 1) if (need_l and dl is not None) else None,
+                None)

