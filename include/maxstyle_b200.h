@@ -61,6 +61,20 @@ enum {
                                        otherwise they are inputs (the reference's cached values) */
 };
 
+/* sweep flags -- performance only: how a streaming kernel walks its tensor and what it tells L2.
+ * The three streaming kernels of one fwd+bwd touch x three times; a caller that runs them back to
+ * back alternates the direction so that each kernel starts where the previous one stopped (those
+ * lines are still in the 126 MB L2) and marks x "keep" while another kernel will re-read it.
+ * MaxStyle.forward/backward use  stats: X_KEEP;  apply: REVERSE | X_KEEP;  bwd: X_STREAM.
+ * REVERSE changes the summation order of stats / bwd (last-bit differences); a fixed choice is
+ * run-to-run deterministic. */
+enum {
+    MAXSTYLE_SWEEP_REVERSE = 1,    /* walk each CTA's slice from its high end                         */
+    MAXSTYLE_SWEEP_X_KEEP = 2,     /* loads of x: L2 evict-last (a later kernel re-reads x)           */
+    MAXSTYLE_SWEEP_X_STREAM = 4,   /* loads of x: L2 evict-first (last use of x)                      */
+    MAXSTYLE_SWEEP_IO_NORMAL = 8   /* y / dy / dx: default L2 policy instead of evict-first            */
+};
+
 /* optimiser step fused into the backward epilogue (north_star item 4) */
 enum {
     MAXSTYLE_STEP_NONE = 0,
@@ -99,7 +113,7 @@ size_t maxstyle_workspace_bytes(int N, int C, int H, int W, int dtype, int layou
  * One pass over x; per-(n,c) plane mean and sqrt(unbiased var + eps) by Welford/Chan
  * merging.  Writes rows [row_offset, row_offset+N) of mu_all / sig_all. */
 int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, int row_offset,
-                   int N, int C, int H, int W, int dtype, int layout, float eps,
+                   int N, int C, int H, int W, int dtype, int layout, float eps, int sweep,
                    void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
 
 /* Table step (replaces maxstyle.py:165-185 on the [N,C] tables): optional batch std,
@@ -114,7 +128,7 @@ int maxstyle_tables(const float* mu_all, const float* sig_all, int table_ld, int
 
 /* Kernel 2 -- apply (replaces the normalise + affine chain, maxstyle.py:161,181-185). */
 int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, int row_offset, const float* scale,
-                   const float* shift, int N, int C, int H, int W, int dtype, int layout,
+                   const float* shift, int N, int C, int H, int W, int dtype, int layout, int sweep,
                    maxstyle_stream_t stream);
 
 /* Whole forward on one GPU (N_global == N): stats -> tables -> apply, one call.
@@ -123,6 +137,7 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig,
                  const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
                  float* gamma_std, float* beta_std, float* scale, float* shift,
                  int N, int C, int H, int W, int dtype, int layout, int flags, float eps,
+                 int stats_sweep, int apply_sweep,
                  void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
 
 /* Kernel 3 -- backward (replaces the autograd graph of maxstyle.py:157-185).
@@ -136,7 +151,7 @@ int maxstyle_bwd(const void* dy, const void* x, void* dx,
                  const float* gamma_std, const float* beta_std, int flags,
                  float* d_gamma, float* d_beta, float* d_lmda,
                  const maxstyle_step_t* step,
-                 int N, int C, int H, int W, int dtype, int layout,
+                 int N, int C, int H, int W, int dtype, int layout, int sweep,
                  void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
 
 /* Stand-alone optimiser step on the three parameter tensors (same arithmetic as the fused

@@ -39,18 +39,14 @@ int check_workspace(const void* ws, size_t bytes, const Workspace& w) {
     return MAXSTYLE_OK;
 }
 
-ItemGeom geom_of(const Plan& p, int64_t M) {
-    ItemGeom g;
-    g.M = M; g.nvec = p.nvec; g.chunk = p.chunk; g.items = p.items; g.splits = p.splits;
+// sweep flags (include/maxstyle_b200.h) -> device geometry
+Sweep sweep_of(const Plan& p, int64_t M, int sweep) {
+    Sweep g;
+    g.M = M; g.nvec = p.nvec; g.planes = p.planes; g.total = p.total; g.per = p.per; g.slots = p.slots;
+    g.reverse = (sweep & MAXSTYLE_SWEEP_REVERSE) ? 1 : 0;
+    g.in_policy = (sweep & MAXSTYLE_SWEEP_X_KEEP) ? kPolicyKeep : ((sweep & MAXSTYLE_SWEEP_X_STREAM) ? kPolicyStream : kPolicyNormal);
+    g.io_policy = (sweep & MAXSTYLE_SWEEP_IO_NORMAL) ? kPolicyNormal : kPolicyStream;
     return g;
-}
-
-int grid_for(const Plan& p, int sms) {
-    const int per_block = kThreads / p.group;
-    int64_t blocks = (p.items + per_block - 1) / per_block;
-    const int64_t cap = (int64_t)sms * kBlocksPerSM;
-    if (blocks > cap) blocks = cap;
-    return (int)(blocks < 1 ? 1 : blocks);
 }
 
 // Vector accesses a thread keeps in flight per tensor: sized so the fp32 copies of the loaded
@@ -63,33 +59,32 @@ template <int VEC, int TENSORS> constexpr int vpt_for() {
 // ---- dispatch on (dtype, vector width, group size) ------------------------------------------
 template <typename T, int VEC, int G>
 void launch_stats(const void* x, float* mu, float* sig, TableRef tr, char* ws, const Workspace& w, const Plan& p, int64_t M,
-                  float eps, int grid, cudaStream_t s) {
-    stats_nchw_kernel<T, VEC, G, vpt_for<VEC, 1>(), Hint::kDefault><<<grid, kThreads, 0, s>>>(
+                  float eps, int sweep, cudaStream_t s) {
+    stats_nchw_kernel<T, VEC, G, vpt_for<VEC, 1>()><<<p.grid, kThreads, 0, s>>>(
         static_cast<const T*>(x), mu, sig, tr, reinterpret_cast<float4*>(ws + w.partials),
-        reinterpret_cast<int*>(ws + w.plane_counters), geom_of(p, M), eps);
+        reinterpret_cast<unsigned long long*>(ws + w.plane_tickets), sweep_of(p, M, sweep), eps);
 }
 
 template <typename T, int VEC, int G>
 void launch_apply(const void* x, void* y, const float* mu, TableRef tr, const float* scale, const float* shift, const Plan& p,
-                  int64_t M, int grid, cudaStream_t s) {
-    apply_nchw_kernel<T, VEC, G, vpt_for<VEC, 1>()><<<grid, kThreads, 0, s>>>(static_cast<const T*>(x), static_cast<T*>(y), mu, tr,
-                                                                              scale, shift, geom_of(p, M));
+                  int64_t M, int sweep, cudaStream_t s) {
+    apply_nchw_kernel<T, VEC, G, vpt_for<VEC, 1>()><<<p.grid, kThreads, 0, s>>>(static_cast<const T*>(x), static_cast<T*>(y), mu, tr,
+                                                                                scale, shift, sweep_of(p, M, sweep));
 }
 
 template <typename T, int VEC, int G>
 void launch_bwd(const void* dy, const void* x, void* dx, char* ws, const Workspace& w, const Plan& p, int64_t M,
-                const BwdTables& tb, const StepArgs& st, int grid, cudaStream_t s) {
+                const BwdTables& tb, const StepArgs& st, int sweep, cudaStream_t s) {
     float4* partials = reinterpret_cast<float4*>(ws + w.partials);
-    int* counters = reinterpret_cast<int*>(ws + w.sample_counters);
+    unsigned long long* tickets = reinterpret_cast<unsigned long long*>(ws + w.sample_tickets);
     int* done = reinterpret_cast<int*>(ws + w.done_counter);
+    const Sweep g = sweep_of(p, M, sweep);
     if (dx)
-        bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), true><<<grid, kThreads, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x),
-                                                                         static_cast<T*>(dx), partials, counters, done,
-                                                                         geom_of(p, M), tb, st);
+        bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), true><<<p.grid, kThreads, 0, s>>>(
+            static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<T*>(dx), partials, tickets, done, g, tb, st);
     else
-        bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), false><<<grid, kThreads, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x),
-                                                                          nullptr, partials, counters, done, geom_of(p, M),
-                                                                          tb, st);
+        bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), false><<<p.grid, kThreads, 0, s>>>(
+            static_cast<const T*>(dy), static_cast<const T*>(x), nullptr, partials, tickets, done, g, tb, st);
 }
 
 #define MS_DISPATCH_G(FN, T, V, plan, ...)                                                         \
@@ -161,7 +156,8 @@ size_t maxstyle_workspace_bytes(int N, int C, int H, int W, int dtype, int layou
 }
 
 int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, int row_offset, int N, int C, int H, int W,
-                   int dtype, int layout, float eps, void* workspace, size_t workspace_bytes, maxstyle_stream_t stream) {
+                   int dtype, int layout, float eps, int sweep, void* workspace, size_t workspace_bytes,
+                   maxstyle_stream_t stream) {
     int rc = check_shape(N, C, H, W, dtype, layout);
     if (rc) return rc;
     if (!x || !mu_all || !sig_all || row_offset < 0 || table_ld < C) return MAXSTYLE_ERR_BAD_ARG;
@@ -170,9 +166,9 @@ int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, i
     if ((rc = check_workspace(workspace, workspace_bytes, w))) return rc;
     const int sms = sm_count();
     if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
-    const Plan p = make_plan(N, C, M, dtype, common_align(x));
+    const Plan p = make_plan(N, C, M, dtype, common_align(x), sms);
     const TableRef tr{C, table_ld, row_offset};
-    MS_DISPATCH(launch_stats, dtype, p, x, mu_all, sig_all, tr, static_cast<char*>(workspace), w, p, M, eps, grid_for(p, sms),
+    MS_DISPATCH(launch_stats, dtype, p, x, mu_all, sig_all, tr, static_cast<char*>(workspace), w, p, M, eps, sweep,
                 static_cast<cudaStream_t>(stream));
     return check_launch();
 }
@@ -192,36 +188,37 @@ int maxstyle_tables(const float* mu_all, const float* sig_all, int table_ld, int
 }
 
 int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, int row_offset, const float* scale,
-                   const float* shift, int N, int C, int H, int W, int dtype, int layout, maxstyle_stream_t stream) {
+                   const float* shift, int N, int C, int H, int W, int dtype, int layout, int sweep,
+                   maxstyle_stream_t stream) {
     int rc = check_shape(N, C, H, W, dtype, layout);
     if (rc) return rc;
     if (!x || !y || !mu_all || !scale || !shift || row_offset < 0 || table_ld < C) return MAXSTYLE_ERR_BAD_ARG;
     const int sms = sm_count();
     if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
     const int64_t M = (int64_t)H * W;
-    const Plan p = make_plan(N, C, M, dtype, common_align(x, y));
+    const Plan p = make_plan(N, C, M, dtype, common_align(x, y), sms);
     const TableRef tr{C, table_ld, row_offset};
-    MS_DISPATCH(launch_apply, dtype, p, x, y, mu_all, tr, scale, shift, p, M, grid_for(p, sms),
+    MS_DISPATCH(launch_apply, dtype, p, x, y, mu_all, tr, scale, shift, p, M, sweep,
                 static_cast<cudaStream_t>(stream));
     return check_launch();
 }
 
 int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* perm, const float* lmda,
                  const float* gamma_noise, const float* beta_noise, float* gamma_std, float* beta_std, float* scale,
-                 float* shift, int N, int C, int H, int W, int dtype, int layout, int flags, float eps, void* workspace,
-                 size_t workspace_bytes, maxstyle_stream_t stream) {
-    int rc = maxstyle_stats(x, mu, sig, C, 0, N, C, H, W, dtype, layout, eps, workspace, workspace_bytes, stream);
+                 float* shift, int N, int C, int H, int W, int dtype, int layout, int flags, float eps, int stats_sweep,
+                 int apply_sweep, void* workspace, size_t workspace_bytes, maxstyle_stream_t stream) {
+    int rc = maxstyle_stats(x, mu, sig, C, 0, N, C, H, W, dtype, layout, eps, stats_sweep, workspace, workspace_bytes, stream);
     if (rc) return rc;
     rc = maxstyle_tables(mu, sig, C, N, 0, N, C, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, flags, scale, shift,
                          stream);
     if (rc) return rc;
-    return maxstyle_apply(x, y, mu, C, 0, scale, shift, N, C, H, W, dtype, layout, stream);
+    return maxstyle_apply(x, y, mu, C, 0, scale, shift, N, C, H, W, dtype, layout, apply_sweep, stream);
 }
 
 int maxstyle_bwd(const void* dy, const void* x, void* dx, const float* mu_all, const float* sig_all, int table_ld, int N_global,
                  int row_offset, const float* scale, const int64_t* perm, const float* lmda, const float* gamma_std,
                  const float* beta_std, int flags, float* d_gamma, float* d_beta, float* d_lmda, const maxstyle_step_t* step,
-                 int N, int C, int H, int W, int dtype, int layout, void* workspace, size_t workspace_bytes,
+                 int N, int C, int H, int W, int dtype, int layout, int sweep, void* workspace, size_t workspace_bytes,
                  maxstyle_stream_t stream) {
     int rc = check_shape(N, C, H, W, dtype, layout);
     if (rc) return rc;
@@ -235,13 +232,13 @@ int maxstyle_bwd(const void* dy, const void* x, void* dx, const float* mu_all, c
     if ((rc = check_workspace(workspace, workspace_bytes, w))) return rc;
     const int sms = sm_count();
     if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
-    const Plan p = make_plan(N, C, M, dtype, common_align(dy, x, dx));
+    const Plan p = make_plan(N, C, M, dtype, common_align(dy, x, dx), sms);
     BwdTables tb;
     tb.mu_all = mu_all; tb.sig_all = sig_all; tb.scale = scale; tb.perm = perm; tb.lmda = lmda;
     tb.gamma_std = gamma_std; tb.beta_std = beta_std; tb.d_gamma = d_gamma; tb.d_beta = d_beta; tb.d_lmda = d_lmda;
     tb.row_offset = row_offset; tb.N = N; tb.C = C; tb.flags = flags; tb.ld = table_ld;
     const StepArgs st = to_step_args(step);
-    MS_DISPATCH(launch_bwd, dtype, p, dy, x, dx, static_cast<char*>(workspace), w, p, M, tb, st, grid_for(p, sms),
+    MS_DISPATCH(launch_bwd, dtype, p, dy, x, dx, static_cast<char*>(workspace), w, p, M, tb, st, sweep,
                 static_cast<cudaStream_t>(stream));
     return check_launch();
 }

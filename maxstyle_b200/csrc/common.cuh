@@ -11,57 +11,52 @@ constexpr int kWarps = kThreads / 32;
 
 // ----------------------------------------------------------------------------------------
 // Vectorised global access.  sm_100 adds 256-bit global loads/stores (SASS LDG.E.256 /
-// STG.E.256) and lets them carry an L2 eviction priority (.L2::evict_first / evict_last), which
-// the 128-bit forms cannot.  Vec<T,VEC> moves VEC elements of T per instruction:
+// STG.E.256).  Every access carries a run-time L2 cache policy (createpolicy + .L2::cache_hint):
+// the host decides per call whether a tensor is streamed (evict-first) or will be re-read by
+// the next kernel of the layer (evict-last), see "sweep flags" in include/maxstyle_b200.h.
+// Vec<T,VEC> moves VEC elements of T per instruction:
 //   32 bytes (8 x f32 / 16 x bf16)  -- the fast path, planes 32-byte aligned
 //   16 bytes (4 x f32 /  8 x bf16)  -- planes only 16-byte aligned
 //   1 element                       -- ragged / unaligned planes
 // and converts to/from fp32 registers.
 // ----------------------------------------------------------------------------------------
-enum class Hint {
-    kDefault,   // no L2 priority
-    kStream,    // last use of the line: evict-first in L2
-    kKeep       // a later phase re-reads it: evict-last in L2
-};
+enum : int { kPolicyNormal = 0, kPolicyStream = 1, kPolicyKeep = 2 };
+
+__device__ __forceinline__ uint64_t make_policy(int kind) {
+    uint64_t p;
+    if (kind == kPolicyStream) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == kPolicyKeep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 
 struct Words8 { uint32_t w[8]; };
 struct Words4 { uint32_t w[4]; };
 
-template <Hint H> __device__ __forceinline__ Words8 ld256(const void* p) {
+__device__ __forceinline__ Words8 ld256(const void* p, uint64_t pol) {
     Words8 r;
-    if constexpr (H == Hint::kStream) {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
-                       "=r"(r.w[7]) : "l"(p));
-    } else if constexpr (H == Hint::kKeep) {
-        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
-                       "=r"(r.w[7]) : "l"(p));
-    } else {
-        asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
-                       "=r"(r.w[7]) : "l"(p));
-    }
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                   "=r"(r.w[7]) : "l"(p), "l"(pol));
     return r;
 }
 
-// streaming store: the line is not read again by this pass, evict-first in L2
-__device__ __forceinline__ void st256_stream(void* p, const Words8& r) {
-    asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+__device__ __forceinline__ void st256(void* p, const Words8& r, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7}, %9;"
                  ::"r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]), "r"(r.w[3]), "r"(r.w[4]), "r"(r.w[5]), "r"(r.w[6]), "r"(r.w[7]),
-                   "l"(p) : "memory");
+                   "l"(p), "l"(pol) : "memory");
 }
 
-__device__ __forceinline__ Words4 ld128(const void* p) {
+__device__ __forceinline__ Words4 ld128(const void* p, uint64_t pol) {
     Words4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "l"(p), "l"(pol));
     return r;
 }
 
-__device__ __forceinline__ void st128_stream(void* p, const Words4& r) {
-    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r.w[0]), "r"(r.w[1]), "r"(r.w[2]), "r"(r.w[3])
-                 : "memory");
+__device__ __forceinline__ void st128(void* p, const Words4& r, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(r.w[0]),
+                 "r"(r.w[1]), "r"(r.w[2]), "r"(r.w[3]), "l"(pol) : "memory");
 }
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
@@ -103,28 +98,28 @@ template <int NW> struct Unpack<__nv_bfloat16, NW> {
 template <typename T, int VEC> struct Vec {
     static constexpr int kBytes = VEC * (int)sizeof(T);
     static_assert(kBytes == 32 || kBytes == 16 || VEC == 1, "unsupported vector width");
-    template <Hint H> static __device__ __forceinline__ void load(const T* p, float (&v)[VEC]) {
+    static __device__ __forceinline__ void load(const T* p, float (&v)[VEC], uint64_t pol) {
         if constexpr (VEC == 1) {
             v[0] = to_f32<T>(__ldg(p));
         } else if constexpr (kBytes == 32) {
-            const Words8 r = ld256<H>(p);
+            const Words8 r = ld256(p, pol);
             Unpack<T, 8>::to(r.w, v);
         } else {
-            const Words4 r = ld128(p);
+            const Words4 r = ld128(p, pol);
             Unpack<T, 4>::to(r.w, v);
         }
     }
-    static __device__ __forceinline__ void store(T* p, const float (&v)[VEC]) {
+    static __device__ __forceinline__ void store(T* p, const float (&v)[VEC], uint64_t pol) {
         if constexpr (VEC == 1) {
             *p = from_f32<T>(v[0]);
         } else if constexpr (kBytes == 32) {
             Words8 r;
             Unpack<T, 8>::from(v, r.w);
-            st256_stream(p, r);
+            st256(p, r, pol);
         } else {
             Words4 r;
             Unpack<T, 4>::from(v, r.w);
-            st128_stream(p, r);
+            st128(p, r, pol);
         }
     }
 };
@@ -141,6 +136,20 @@ __device__ __forceinline__ Moments merge(const Moments a, const Moments b) {
     const float n = a.n + b.n;
     if (n == 0.f) return a;
     const float w = b.n / n;                  // IEEE division: these merges are off the per-element path
+    const float d = b.mean - a.mean;
+    Moments r;
+    r.n = n;
+    r.mean = fmaf(d, w, a.mean);
+    r.m2 = a.m2 + b.m2 + d * d * a.n * w;
+    return r;
+}
+
+// Per-thread running merge on the per-element path: the weight b.n/n only has to be a consistent
+// approximation (both uses see the same w), so the fast reciprocal is enough.
+__device__ __forceinline__ Moments merge_fast(const Moments a, const Moments b) {
+    const float n = a.n + b.n;
+    if (b.n == 0.f) return a;
+    const float w = __fdividef(b.n, n);
     const float d = b.mean - a.mean;
     Moments r;
     r.n = n;
@@ -220,27 +229,29 @@ template <int G> __device__ __forceinline__ void group_sync() {
     if constexpr (G > 32) __syncthreads(); else __syncwarp();
 }
 
-// "Last arriver" ticket: every group bumps `counter` after publishing its partial result;
-// the group that observes `total-1` owns the merge.  The winner resets the counter so the
-// workspace is left zeroed for the next call (see include/maxstyle_b200.h).
-template <int G> __device__ __forceinline__ bool arrive_is_last(int* counter, int total, Scratch& s) {
-    const int lane_in_group = G > 32 ? threadIdx.x : (threadIdx.x & 31);
-    int last = 0;
-    if (lane_in_group == 0) {
-        __threadfence();                                   // release: partial is visible before the ticket
-        const int prev = atomicAdd(counter, 1);
-        last = (prev == total - 1);
-        if (last) { *counter = 0; __threadfence(); }       // acquire side + reset
-    }
+// Weighted "last arriver" ticket (called by ONE thread of a group): after publishing its partial
+// result the group adds the amount of work it finished to `counter`; whoever brings the counter
+// to `total` owns the merge.  The winner resets the counter, so the workspace is left zeroed
+// for the next call (see include/maxstyle_b200.h).
+__device__ __forceinline__ bool ticket_add(unsigned long long* counter, unsigned long long amount,
+                                           unsigned long long total) {
+    __threadfence();                                       // release: the partial is visible before the ticket
+    const unsigned long long prev = atomicAdd(counter, amount);
+    const bool last = (prev + amount == total);
+    if (last) { *counter = 0ull; __threadfence(); }        // reset + acquire side
+    return last;
+}
+
+// Broadcast a flag computed by the group's first thread to the whole group.
+template <int G> __device__ __forceinline__ bool group_bcast(bool flag, Scratch& s) {
     if constexpr (G > 32) {
         __syncthreads();
-        if (threadIdx.x == 0) s.flag = last;
+        if (threadIdx.x == 0) s.flag = flag;
         __syncthreads();
-        last = s.flag;
+        return s.flag != 0;
     } else {
-        last = __shfl_sync(0xffffffffu, last, 0);
+        return __shfl_sync(0xffffffffu, (int)flag, 0) != 0;
     }
-    return last != 0;
 }
 
 }  // namespace ms

@@ -1,11 +1,14 @@
 // Streaming kernels for NCHW-contiguous feature maps: every (n,c) plane is M = H*W contiguous
-// elements.  A work item is (plane, split): `chunk` 16-byte vectors of one plane, handled by a
-// group of G threads (a warp for small planes, the whole CTA otherwise).  Grids are persistent:
-// 148 SMs x kBlocksPerSM CTAs stride over the item list, so neighbouring CTAs touch neighbouring
-// memory at the same time and there is no per-item CTA launch cost.
+// elements = nvec vector accesses.  The tensor is swept as one flat space of planes*nvec
+// vectors (see plan.h): a CTA owns a contiguous slice cut into pieces at plane boundaries
+// (CTA mode), or a warp owns whole small planes (warp mode).  Per piece the group reduces once;
+// planes shared by several CTAs are merged from per-CTA partials in a fixed order by whoever
+// arrives last (weighted tickets, no float atomics), so results are run-to-run deterministic.
 #pragma once
 #include "common.cuh"
 #include "plan.h"
+
+#define MS_HD __host__ __device__ __forceinline__
 
 namespace ms {
 
@@ -21,111 +24,197 @@ struct TableRef {
     }
 };
 
-struct ItemGeom {
+// Geometry of one sweep (device copy of Plan + per-call options).
+struct Sweep {
     int64_t M;        // elements per plane
     int64_t nvec;     // vectors per plane
-    int64_t chunk;    // vectors per item
-    int64_t items;    // planes * splits
-    int splits;
+    int64_t planes;   // N*C
+    int64_t total;    // planes*nvec
+    int64_t per;      // CTA mode: vectors per CTA; warp mode: planes per warp
+    int slots;        // partial slots per plane
+    int reverse;      // walk the slice from its high end (so that the kernel that follows a forward
+                      // sweep over the same tensor meets the lines that are still in L2 first)
+    int in_policy;    // L2 policy of the loads of the tensor that other kernels of the layer re-read (x)
+    int io_policy;    // L2 policy of everything else (dy loads, y / dx stores)
 };
 
 template <int G> struct GroupIdx {
     static constexpr int kPerBlock = kThreads / G;
     __device__ static __forceinline__ int lane() { return G > 32 ? threadIdx.x : (threadIdx.x & 31); }
-    __device__ static __forceinline__ int64_t first() {
+    __device__ static __forceinline__ int64_t index() {
         return (int64_t)blockIdx.x * kPerBlock + (G > 32 ? 0 : (threadIdx.x >> 5));
     }
-    __device__ static __forceinline__ int64_t stride() { return (int64_t)gridDim.x * kPerBlock; }
 };
+
+struct Piece {
+    int64_t plane;    // plane index
+    int v0, v1;       // vector range inside the plane (planes hold < 2^31 vectors)
+};
+
+// The pieces of one group's slice, in sweep order.
+template <int G> struct PieceIter {
+    int64_t lo, hi, nvec;
+    bool reverse;
+    // gi: index of the group (CTA index in CTA mode, global warp index in warp mode)
+    MS_HD PieceIter(const Sweep& g, int64_t gi) {
+        const int64_t unit = G > 32 ? 1 : g.nvec;             // warp mode: the slice is whole planes
+        lo = gi * g.per * unit;
+        hi = lo + g.per * unit < g.total ? lo + g.per * unit : g.total;
+        nvec = g.nvec;
+        reverse = g.reverse != 0;
+    }
+    MS_HD bool next(Piece& p) {
+        if (lo >= hi) return false;
+        if (!reverse) {
+            p.plane = lo / nvec;
+            const int64_t v0 = lo - p.plane * nvec;
+            const int64_t v1 = v0 + (hi - lo) < nvec ? v0 + (hi - lo) : nvec;
+            p.v0 = (int)v0; p.v1 = (int)v1;
+            lo += v1 - v0;
+        } else {
+            p.plane = (hi - 1) / nvec;
+            const int64_t v1 = hi - p.plane * nvec;
+            const int64_t v0 = v1 - (hi - lo) > 0 ? v1 - (hi - lo) : 0;
+            p.v0 = (int)v0; p.v1 = (int)v1;
+            hi -= v1 - v0;
+        }
+        return true;
+    }
+};
+
+// A piece [v0, v1) is walked in batches of G*VPT vectors: `full` whole batches (no bounds checks in
+// the hot loop) and one ragged batch at the far end of the walk.  batch_begin() gives the first
+// vector of batch i for this sweep direction; the ragged batch is i == full.
+template <int G, int VPT> struct Batches {
+    static constexpr int kStep = G * VPT;
+    int v0, v1, full, rem;
+    bool reverse;
+    MS_HD Batches(const Piece& p, bool rev) : v0(p.v0), v1(p.v1), reverse(rev) {
+        const int len = p.v1 - p.v0;
+        full = len / kStep;
+        rem = len - full * kStep;
+    }
+    MS_HD int begin(int i) const { return reverse ? v1 - (i + 1) * kStep : v0 + i * kStep; }
+    // ragged batch: vectors [lo, hi)
+    MS_HD int ragged_lo() const { return reverse ? v0 : v0 + full * kStep; }
+    MS_HD int ragged_hi() const { return reverse ? v0 + rem : v1; }
+};
+
+// Which CTAs share a plane (CTA mode): CTA b covers vectors [b*per, (b+1)*per).
+struct PlaneShare {
+    int64_t first;    // first CTA touching the plane
+    int count;        // number of CTAs touching it
+};
+MS_HD PlaneShare plane_share(const Sweep& g, int64_t plane) {
+    PlaneShare s;
+    s.first = (plane * g.nvec) / g.per;
+    s.count = (int)(((plane + 1) * g.nvec - 1) / g.per - s.first) + 1;
+    return s;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Kernel 1: instance statistics.  Replaces x.mean(dim=[2,3]) / x.var(dim=[2,3]) / sqrt(var+eps)
 // of the reference (src/advanced/maxstyle.py:157-159) with ONE read of x.
-// Per thread: batches of VPT vectors are reduced two-pass in registers (sum -> mean -> squared
-// deviations) and folded into a running (n, mean, M2) with the Chan/Welford merge; then warp
-// shuffles, then shared memory across the CTA's warps, then (splits > 1) a last-arriver merge
-// of the per-item partials in fixed order, so results are run-to-run deterministic.
+// Numerics: every value is first shifted by K = the plane's first element (exact for data whose
+// spread is small against its mean -- the case where fp32 moments lose digits), then per thread
+// batches of VPT vectors are reduced two-pass in registers (sum -> mean -> squared deviations) and
+// folded into a running (n, mean, M2) with the Chan/Welford merge; warp shuffles, shared memory
+// across the CTA's warps, and for planes shared by several CTAs a fixed-order merge of the
+// per-CTA partials by the last arriver.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VEC, int G, int VPT, Hint LOAD>
+template <typename T, int VEC, int G, int VPT>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 stats_nchw_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __restrict__ sig, TableRef tr,
-                  float4* __restrict__ partials, int* __restrict__ plane_counters, ItemGeom g, float eps) {
+                  float4* __restrict__ partials, unsigned long long* __restrict__ plane_tickets, Sweep g, float eps) {
     __shared__ Scratch scratch;
     const int t = GroupIdx<G>::lane();
+    const uint64_t pol = make_policy(g.in_policy);
     const float inv_m1 = 1.0f / (float)(g.M - 1);
-    for (int64_t item = GroupIdx<G>::first(); item < g.items; item += GroupIdx<G>::stride()) {
-        const int64_t plane = item / g.splits;
-        const int split = (int)(item - plane * g.splits);
-        const int64_t v_begin = (int64_t)split * g.chunk;
-        const int64_t v_end = min(g.nvec, v_begin + g.chunk);
-        const T* base = x + plane * g.M;
+    constexpr int kTail = VPT > 1 ? VPT / 2 : 1;
+    PieceIter<G> it(g, GroupIdx<G>::index());
+    Piece pc;
+    while (it.next(pc)) {
+        const T* base = x + pc.plane * g.M;
+        const float K = to_f32<T>(__ldg(base));
         Moments acc{0.f, 0.f, 0.f};
-        for (int64_t v0 = v_begin + t; v0 < v_end; v0 += (int64_t)G * VPT) {
+        const int len = pc.v1 - pc.v0;
+        const Batches<G, VPT> bt(pc, g.reverse != 0);
+        for (int i = 0; i < bt.full; ++i) {            // whole batches: constant count, no bounds checks
+            const T* p = base + (int64_t)(bt.begin(i) + t) * VEC;
             float val[VPT][VEC];
-            bool ok[VPT];
 #pragma unroll
-            for (int j = 0; j < VPT; ++j) {
-                const int64_t idx = v0 + (int64_t)j * G;
-                ok[j] = idx < v_end;
-                if (ok[j]) {
-                    Vec<T, VEC>::template load<LOAD>(base + idx * VEC, val[j]);
-                } else {
+            for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(p + (int64_t)j * G * VEC, val[j], pol);
+            float s = 0.f;
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) val[j][k] = 0.f;
-                }
-            }
+            for (int j = 0; j < VPT; ++j)
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) { val[j][k] -= K; s += val[j][k]; }
             Moments b;
-            if (ok[VPT - 1]) {                         // full batch: constant count
-                float s = 0.f;
+            b.n = (float)(VPT * VEC);
+            b.mean = s * (1.0f / (float)(VPT * VEC));
+            float q = 0.f;
 #pragma unroll
-                for (int j = 0; j < VPT; ++j)
+            for (int j = 0; j < VPT; ++j)
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) s += val[j][k];
-                b.n = (float)(VPT * VEC);
-                b.mean = s * (1.0f / (float)(VPT * VEC));
-                float q = 0.f;
+                for (int k = 0; k < VEC; ++k) { const float d = val[j][k] - b.mean; q = fmaf(d, d, q); }
+            b.m2 = q;
+            acc = merge_fast(acc, b);
+        }
+        if (bt.rem) {                                  // ragged end of the piece: < G*VPT vectors, kTail loads in flight
+            const int hi = bt.ragged_hi();
+            for (int lo = bt.ragged_lo() + t; lo < hi; lo += kTail * G) {
+                float val[kTail][VEC];
 #pragma unroll
-                for (int j = 0; j < VPT; ++j)
+                for (int j = 0; j < kTail; ++j)
+                    if (lo + j * G < hi) Vec<T, VEC>::load(base + (int64_t)(lo + j * G) * VEC, val[j], pol);
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) { const float d = val[j][k] - b.mean; q = fmaf(d, d, q); }
-                b.m2 = q;
-            } else {                                   // ragged tail of the item
-                float s = 0.f, cnt = 0.f;
+                for (int j = 0; j < kTail; ++j) {
+                    if (lo + j * G < hi) {             // each vector is its own mini-batch
+                        float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < VPT; ++j) {
-                    cnt += ok[j] ? (float)VEC : 0.f;
+                        for (int k = 0; k < VEC; ++k) { val[j][k] -= K; s += val[j][k]; }
+                        Moments b;
+                        b.n = (float)VEC;
+                        b.mean = s * (1.0f / (float)VEC);
+                        float q = 0.f;
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) s += val[j][k];
+                        for (int k = 0; k < VEC; ++k) { const float d = val[j][k] - b.mean; q = fmaf(d, d, q); }
+                        b.m2 = q;
+                        acc = merge_fast(acc, b);
+                    }
                 }
-                b.n = cnt;
-                b.mean = s / cnt;
-                float q = 0.f;
-#pragma unroll
-                for (int j = 0; j < VPT; ++j)
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) { const float d = ok[j] ? val[j][k] - b.mean : 0.f; q = fmaf(d, d, q); }
-                b.m2 = q;
             }
-            acc = merge(acc, b);
         }
         const Moments tot = group_merge<G>(acc, scratch);
-        if (g.splits == 1) {
+        if (len == g.nvec) {                           // the piece is the whole plane
             if (t == 0) {
-                const int64_t o = tr.at(plane);
-                mu[o] = tot.mean;
+                const int64_t o = tr.at(pc.plane);
+                mu[o] = K + tot.mean;
                 sig[o] = sqrtf(tot.m2 * inv_m1 + eps);
             }
-        } else {
-            if (t == 0) partials[item] = make_float4(tot.n, tot.mean, tot.m2, 0.f);
-            if (arrive_is_last<G>(&plane_counters[plane], g.splits, scratch)) {
-                if (t == 0) {
-                    Moments m{0.f, 0.f, 0.f};
-                    for (int s = 0; s < g.splits; ++s) {
-                        const float4 p = __ldcg(&partials[plane * g.splits + s]);
-                        m = merge(m, Moments{p.x, p.y, p.z});
+        } else if (t < 32) {                           // CTA mode only: warp 0 publishes, the last arriver merges
+            const PlaneShare sh = plane_share(g, pc.plane);
+            float4* slot = partials + pc.plane * g.slots;
+            bool last = false;
+            if (t == 0) {
+                slot[blockIdx.x - sh.first] = make_float4(tot.n, tot.mean, tot.m2, 0.f);
+                last = ticket_add(&plane_tickets[pc.plane], (unsigned long long)len, (unsigned long long)g.nvec);
+            }
+            last = __shfl_sync(0xffffffffu, (int)last, 0) != 0;
+            __syncwarp();
+            if (last) {
+                Moments m{0.f, 0.f, 0.f};
+                for (int k0 = 0; k0 < sh.count; k0 += 32) {           // fixed order: slot index, then a shuffle tree
+                    Moments p{0.f, 0.f, 0.f};
+                    if (k0 + t < sh.count) {
+                        const float4 v = __ldcg(&slot[k0 + t]);
+                        p = Moments{v.x, v.y, v.z};
                     }
-                    const int64_t o = tr.at(plane);
-                    mu[o] = m.mean;
+                    m = merge(m, warp_merge(p));
+                }
+                if (t == 0) {
+                    const int64_t o = tr.at(pc.plane);
+                    mu[o] = K + m.mean;
                     sig[o] = sqrtf(m.m2 * inv_m1 + eps);
                 }
             }
@@ -136,36 +225,45 @@ stats_nchw_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
 // ---------------------------------------------------------------------------------------------
 // Kernel 2: apply.  y = (x - mu) * scale + shift with scale = A/sig, shift = B, i.e. the
 // normalise + mix + perturb + affine chain of maxstyle.py:161,172-185 folded into one FMA per
-// element (the [N,C] tables come from tables_kernel).  x is read for the last time (evict-first),
-// y is written with streaming stores.
+// element (the [N,C] tables come from tables_kernel).
 // ---------------------------------------------------------------------------------------------
 template <typename T, int VEC, int G, int VPT>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 apply_nchw_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ mu, TableRef tr,
-                  const float* __restrict__ scale, const float* __restrict__ shift, ItemGeom g) {
+                  const float* __restrict__ scale, const float* __restrict__ shift, Sweep g) {
     const int t = GroupIdx<G>::lane();
-    for (int64_t item = GroupIdx<G>::first(); item < g.items; item += GroupIdx<G>::stride()) {
-        const int64_t plane = item / g.splits;
-        const int split = (int)(item - plane * g.splits);
-        const int64_t v_begin = (int64_t)split * g.chunk;
-        const int64_t v_end = min(g.nvec, v_begin + g.chunk);
-        const T* src = x + plane * g.M;
-        T* dst = y + plane * g.M;
-        const float m = __ldg(mu + tr.at(plane)), a = __ldg(scale + plane), b = __ldg(shift + plane);
-        for (int64_t v0 = v_begin + t; v0 < v_end; v0 += (int64_t)G * VPT) {
+    const uint64_t pol_in = make_policy(g.in_policy), pol_out = make_policy(g.io_policy);
+    PieceIter<G> it(g, GroupIdx<G>::index());
+    Piece pc;
+    while (it.next(pc)) {
+        const T* src = x + pc.plane * g.M;
+        T* dst = y + pc.plane * g.M;
+        const float m = __ldg(mu + tr.at(pc.plane)), a = __ldg(scale + pc.plane), b = __ldg(shift + pc.plane);
+        const Batches<G, VPT> bt(pc, g.reverse != 0);
+        for (int i = 0; i < bt.full; ++i) {
+            const int64_t o = (int64_t)(bt.begin(i) + t) * VEC;
             float val[VPT][VEC];
 #pragma unroll
-            for (int j = 0; j < VPT; ++j) {
-                const int64_t idx = v0 + (int64_t)j * G;
-                if (idx < v_end) Vec<T, VEC>::template load<Hint::kStream>(src + idx * VEC, val[j]);
-            }
+            for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(src + o + (int64_t)j * G * VEC, val[j], pol_in);
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
-                const int64_t idx = v0 + (int64_t)j * G;
-                if (idx < v_end) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) val[j][k] = fmaf(val[j][k] - m, a, b);
+                Vec<T, VEC>::store(dst + o + (int64_t)j * G * VEC, val[j], pol_out);
+            }
+        }
+        if (bt.rem) {
+            const int lo = bt.ragged_lo() + t, hi = bt.ragged_hi();
+            float val[VPT][VEC];
+#pragma unroll
+            for (int j = 0; j < VPT; ++j)
+                if (lo + j * G < hi) Vec<T, VEC>::load(src + (int64_t)(lo + j * G) * VEC, val[j], pol_in);
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+                if (lo + j * G < hi) {
 #pragma unroll
                     for (int k = 0; k < VEC; ++k) val[j][k] = fmaf(val[j][k] - m, a, b);
-                    Vec<T, VEC>::store(dst + idx * VEC, val[j]);
+                    Vec<T, VEC>::store(dst + (int64_t)(lo + j * G) * VEC, val[j], pol_out);
                 }
             }
         }
@@ -230,8 +328,9 @@ __device__ __forceinline__ void step_update(int mode, int maximize, const StepCo
 // graph of :161-185 collapses to   dx = dy * A/sig,   dA = sum dy*(x-mu)/sig,   dB = sum dy
 // per plane, followed by tiny per-sample reductions.  One sweep reads
 // dy and x once and writes dx once (template DX=false when x does not require grad).  The group
-// finishing the last item of a sample runs the epilogue for that sample: parameter gradients,
-// the channel reduction for d_lmda in fixed order (no float atomics) and the fused optimiser step.
+// that completes a sample (weighted ticket over its C*nvec vectors) runs that sample's epilogue:
+// parameter gradients, the channel reduction for d_lmda in fixed order (no float atomics) and
+// the fused optimiser step.
 // ---------------------------------------------------------------------------------------------
 struct BwdTables {
     const float* mu_all;
@@ -248,35 +347,47 @@ struct BwdTables {
 };
 
 template <int G>
-__device__ __forceinline__ void bwd_finalize_sample(int n, const BwdTables& tb, const StepArgs& st,
-                                                    const float4* partials, int splits, int* done_counter,
-                                                    Scratch& scratch) {
+__device__ __forceinline__ void bwd_finalize_sample(int n, const BwdTables& tb, const StepArgs& st, const Sweep& g,
+                                                    const float4* partials, int* done_counter, Scratch& scratch) {
+    // CTA mode: one warp per channel, its lanes over the CTAs that shared the plane;
+    // warp mode: one lane per channel (every plane has exactly one partial).
+    constexpr int kSub = G > 32 ? 32 : 1;                  // lanes cooperating on one channel
     const int t = GroupIdx<G>::lane();
+    const int sub = t / kSub, sl = t % kSub;
     const int C = tb.C;
     const int64_t row = (int64_t)tb.row_offset + n;
     const bool mix = tb.flags & 1, no_noise = tb.flags & 2;
     const int64_t prow = mix ? tb.perm[row] : row;
-    StepCoef coef = step_coef(st);
+    const StepCoef coef = step_coef(st);
+    const int ld = tb.ld;
     float lam_acc = 0.f, unused = 0.f;
-    for (int c = t; c < C; c += G) {
-        const int64_t plane = (int64_t)n * C + c;
+    for (int c0 = 0; c0 < C; c0 += G / kSub) {
+        const int c = c0 + sub;
         float s1 = 0.f, s2 = 0.f;
-        for (int s = 0; s < splits; ++s) {
-            const float4 p = __ldcg(&partials[plane * splits + s]);
-            s1 += p.x;
-            s2 += p.y;
+        const int64_t plane = (int64_t)n * C + c;
+        if (c < C) {
+            int count = 1;
+            if constexpr (G > 32) count = plane_share(g, plane).count;
+            const float4* slot = partials + plane * g.slots;
+            for (int k = sl; k < count; k += kSub) {
+                const float4 p = __ldcg(&slot[k]);
+                s1 += p.x;
+                s2 += p.y;
+            }
         }
-        const int ld = tb.ld;
-        const float sg = tb.sig_all[row * ld + c], m = tb.mu_all[row * ld + c];
-        const float dA = s2 / sg, dB = s1;
-        const float gg = no_noise ? 0.f : dA * tb.gamma_std[c];
-        const float gb = no_noise ? 0.f : dB * tb.beta_std[c];
-        if (tb.d_gamma) tb.d_gamma[plane] = gg;
-        if (tb.d_beta) tb.d_beta[plane] = gb;
-        if (mix) lam_acc += dA * (tb.sig_all[prow * ld + c] - sg) + dB * (tb.mu_all[prow * ld + c] - m);
-        if (st.mode != 0 && st.update_noise) {
-            step_update(st.mode, st.maximize, coef, gg, st.gamma_noise + plane, st.gamma_m + plane, st.gamma_v + plane);
-            step_update(st.mode, st.maximize, coef, gb, st.beta_noise + plane, st.beta_m + plane, st.beta_v + plane);
+        if constexpr (kSub > 1) { s1 = warp_sum(s1); s2 = warp_sum(s2); }
+        if (c < C && sl == 0) {
+            const float sg = tb.sig_all[row * ld + c], m = tb.mu_all[row * ld + c];
+            const float dA = s2 / sg, dB = s1;
+            const float gg = no_noise ? 0.f : dA * tb.gamma_std[c];
+            const float gb = no_noise ? 0.f : dB * tb.beta_std[c];
+            if (tb.d_gamma) tb.d_gamma[plane] = gg;
+            if (tb.d_beta) tb.d_beta[plane] = gb;
+            if (mix) lam_acc += dA * (tb.sig_all[prow * ld + c] - sg) + dB * (tb.mu_all[prow * ld + c] - m);
+            if (st.mode != 0 && st.update_noise) {
+                step_update(st.mode, st.maximize, coef, gg, st.gamma_noise + plane, st.gamma_m + plane, st.gamma_v + plane);
+                step_update(st.mode, st.maximize, coef, gb, st.beta_noise + plane, st.beta_m + plane, st.beta_v + plane);
+            }
         }
     }
     group_sum2<G>(lam_acc, unused, scratch);
@@ -302,34 +413,34 @@ __device__ __forceinline__ void bwd_finalize_sample(int n, const BwdTables& tb, 
 template <typename T, int VEC, int G, int VPT, bool DX>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 bwd_nchw_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, float4* __restrict__ partials,
-                int* __restrict__ sample_counters, int* __restrict__ done_counter, ItemGeom g, BwdTables tb,
+                unsigned long long* __restrict__ sample_tickets, int* __restrict__ done_counter, Sweep g, BwdTables tb,
                 StepArgs st) {
     __shared__ Scratch scratch;
     const int t = GroupIdx<G>::lane();
-    for (int64_t item = GroupIdx<G>::first(); item < g.items; item += GroupIdx<G>::stride()) {
-        const int64_t plane = item / g.splits;
-        const int split = (int)(item - plane * g.splits);
-        const int64_t v_begin = (int64_t)split * g.chunk;
-        const int64_t v_end = min(g.nvec, v_begin + g.chunk);
-        const T* gsrc = dy + plane * g.M;
-        const T* xsrc = x + plane * g.M;
-        T* dst = DX ? dx + plane * g.M : nullptr;
-        const int n = (int)(plane / tb.C);
-        const float m = __ldg(tb.mu_all + ((int64_t)tb.row_offset + n) * tb.ld + (plane - (int64_t)n * tb.C));
-        const float a = __ldg(tb.scale + plane);
+    const uint64_t pol_x = make_policy(g.in_policy), pol_io = make_policy(g.io_policy);
+    const unsigned long long sample_total = (unsigned long long)tb.C * (unsigned long long)g.nvec;
+    PieceIter<G> it(g, GroupIdx<G>::index());
+    Piece pc;
+    int pending_n = -1;                    // sample whose finished vectors have not been ticketed yet
+    unsigned long long pending = 0;
+    bool more = it.next(pc);
+    while (more) {
+        const T* gsrc = dy + pc.plane * g.M;
+        const T* xsrc = x + pc.plane * g.M;
+        T* dst = DX ? dx + pc.plane * g.M : nullptr;
+        const int n = (int)(pc.plane / tb.C);
+        const float m = __ldg(tb.mu_all + ((int64_t)tb.row_offset + n) * tb.ld + (pc.plane - (int64_t)n * tb.C));
+        const float a = __ldg(tb.scale + pc.plane);
         float s1 = 0.f, s2 = 0.f;
-        for (int64_t v0 = v_begin + t; v0 < v_end; v0 += (int64_t)G * VPT) {
+        const int len = pc.v1 - pc.v0;
+        const Batches<G, VPT> bt(pc, g.reverse != 0);
+        for (int i = 0; i < bt.full; ++i) {
+            const int64_t o = (int64_t)(bt.begin(i) + t) * VEC;
             float gv[VPT][VEC], xv[VPT][VEC];
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
-                const int64_t idx = v0 + (int64_t)j * G;
-                if (idx < v_end) {
-                    Vec<T, VEC>::template load<Hint::kStream>(gsrc + idx * VEC, gv[j]);
-                    Vec<T, VEC>::template load<Hint::kStream>(xsrc + idx * VEC, xv[j]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) { gv[j][k] = 0.f; xv[j][k] = m; }
-                }
+                Vec<T, VEC>::load(gsrc + o + (int64_t)j * G * VEC, gv[j], pol_io);
+                Vec<T, VEC>::load(xsrc + o + (int64_t)j * G * VEC, xv[j], pol_x);
             }
             float b1 = 0.f, b2 = 0.f;
 #pragma unroll
@@ -340,21 +451,51 @@ bwd_nchw_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict
                     b2 = fmaf(gv[j][k], xv[j][k] - m, b2);
                 }
                 if constexpr (DX) {
-                    const int64_t idx = v0 + (int64_t)j * G;
-                    if (idx < v_end) {
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k) gv[j][k] *= a;
-                        Vec<T, VEC>::store(dst + idx * VEC, gv[j]);
-                    }
+                    for (int k = 0; k < VEC; ++k) gv[j][k] *= a;
+                    Vec<T, VEC>::store(dst + o + (int64_t)j * G * VEC, gv[j], pol_io);
                 }
             }
             s1 += b1;
             s2 += b2;
         }
+        if (bt.rem) {
+            const int hi = bt.ragged_hi();
+            for (int lo = bt.ragged_lo() + t; lo < hi; lo += G) {
+                float gv[VEC], xv[VEC];
+                Vec<T, VEC>::load(gsrc + (int64_t)lo * VEC, gv, pol_io);
+                Vec<T, VEC>::load(xsrc + (int64_t)lo * VEC, xv, pol_x);
+                float b1 = 0.f, b2 = 0.f;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    b1 += gv[k];
+                    b2 = fmaf(gv[k], xv[k] - m, b2);
+                }
+                if constexpr (DX) {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) gv[k] *= a;
+                    Vec<T, VEC>::store(dst + (int64_t)lo * VEC, gv, pol_io);
+                }
+                s1 += b1;
+                s2 += b2;
+            }
+        }
         group_sum2<G>(s1, s2, scratch);
-        if (t == 0) partials[item] = make_float4(s1, s2, 0.f, 0.f);
-        if (arrive_is_last<G>(&sample_counters[n], tb.C * g.splits, scratch))
-            bwd_finalize_sample<G>(n, tb, st, partials, g.splits, done_counter, scratch);
+        if (t == 0) {
+            int k = 0;
+            if constexpr (G > 32) k = (int)(blockIdx.x - plane_share(g, pc.plane).first);
+            partials[pc.plane * g.slots + k] = make_float4(s1, s2, 0.f, 0.f);
+        }
+        pending_n = n;
+        pending += (unsigned long long)len;
+        more = it.next(pc);
+        // ticket the finished vectors once per (group, sample): when the sample changes or the slice ends
+        if (!more || (int)(pc.plane / tb.C) != pending_n) {
+            bool last = false;
+            if (t == 0) last = ticket_add(&sample_tickets[pending_n], pending, sample_total);
+            if (group_bcast<G>(last, scratch)) bwd_finalize_sample<G>(pending_n, tb, st, g, partials, done_counter, scratch);
+            pending = 0;
+        }
     }
 }
 

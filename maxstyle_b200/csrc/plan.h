@@ -1,4 +1,13 @@
 // Host-side work decomposition shared by the C API and the workspace query.
+//
+// A tensor of `planes` = N*C planes of `nvec` vector accesses each is swept as ONE flat index
+// space of planes*nvec vectors:
+//   group == 256 (CTA mode):  CTA b owns vectors [b*per, (b+1)*per) -- a contiguous ~total/grid
+//       slice that is cut into "pieces" at plane boundaries.  Work is balanced to one vector
+//       whatever the plane size, a CTA reduces across its threads once per piece (not once per
+//       32 KB), and a plane is shared by at most `slots` CTAs, each writing one partial.
+//   group == 32 (warp mode, small planes):  warp w owns whole planes [w*per, (w+1)*per); no
+//       block-wide synchronisation at all.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -6,26 +15,30 @@
 namespace ms {
 
 constexpr int kBlocksPerSM = 4;                 // 4 x 256 threads resident per SM for the streaming kernels
-constexpr int kVPT = 4;                         // vector accesses a thread keeps in flight per tensor
-constexpr int64_t kWarpPlaneVecs = 512;         // planes up to this many vectors are handled by one warp
-constexpr int kMaxSplits = 256;
+constexpr int kThreadsPerBlock = 256;
+constexpr int kMaxGrid = 2048;                  // workspace is sized for grids up to this (148 SMs x 4 = 592)
+constexpr int64_t kWarpPlaneVecs = 512;         // planes up to this many vectors always go to single warps
+constexpr int64_t kWarpPlaneVecsMany = 4096;    // ... and up to this many when there are >= 2 planes per warp
 
 struct Plan {
-    int vec;          // elements per vector access: 16 B / sizeof(T), or 1 (scalar fallback)
-    int group;        // threads cooperating on one item: 32 (small planes) or 256
-    int splits;       // items per plane
+    int vec;          // elements per vector access: 32 B or 16 B / sizeof(T), or 1 (scalar fallback)
+    int group;        // threads cooperating on one piece: 32 (small planes) or 256
+    int grid;         // CTAs to launch
+    int slots;        // partial-result slots per plane (max number of CTAs sharing a plane)
     int64_t nvec;     // vectors per plane
-    int64_t chunk;    // vectors per item (last item of a plane may be shorter)
     int64_t planes;   // N*C
-    int64_t items;    // planes*splits
+    int64_t total;    // planes*nvec
+    int64_t per;      // CTA mode: vectors per CTA;  warp mode: planes per warp
 };
 
 inline int elem_size(int dtype) { return dtype == 0 ? 4 : 2; }
 
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
 // `align`: the largest power of two (<= 32) dividing every tensor base address involved.
 // A plane is vector-accessible when the base is aligned and its byte size is a multiple of the
 // vector width (then every plane start is aligned too).
-inline Plan make_plan(int N, int C, int64_t M, int dtype, int align) {
+inline Plan make_plan(int N, int C, int64_t M, int dtype, int align, int sms) {
     Plan p;
     const int es = elem_size(dtype);
     if (align >= 32 && (M * es) % 32 == 0) p.vec = 32 / es;
@@ -33,42 +46,49 @@ inline Plan make_plan(int N, int C, int64_t M, int dtype, int align) {
     else p.vec = 1;
     p.nvec = M / p.vec;
     p.planes = (int64_t)N * C;
-    p.group = p.nvec <= kWarpPlaneVecs ? 32 : 256;
-    // an item is one batch of group*kVPT vectors (32 KB with 256-bit vectors and a CTA group);
-    // planes up to two batches stay whole.
-    const int64_t batch = (int64_t)p.group * kVPT;
-    int64_t chunk = p.nvec;
-    if (p.group == 256 && p.nvec > 2 * batch) chunk = batch;
-    int64_t s = (p.nvec + chunk - 1) / chunk;
-    if (s > kMaxSplits) { chunk = ((p.nvec + kMaxSplits - 1) / kMaxSplits + batch - 1) / batch * batch; s = (p.nvec + chunk - 1) / chunk; }
-    p.splits = (int)s;
-    p.chunk = chunk;
-    p.items = p.planes * s;
+    p.total = p.planes * p.nvec;
+    int64_t max_ctas = (int64_t)sms * kBlocksPerSM;
+    if (max_ctas > kMaxGrid) max_ctas = kMaxGrid;
+    const int64_t max_warps = max_ctas * (kThreadsPerBlock / 32);
+    const bool warp_mode = p.nvec <= kWarpPlaneVecs || (p.nvec <= kWarpPlaneVecsMany && p.planes >= 2 * max_warps);
+    if (warp_mode) {
+        p.group = 32;
+        p.per = ceil_div(p.planes, max_warps);
+        const int64_t warps = ceil_div(p.planes, p.per);
+        p.grid = (int)ceil_div(warps, kThreadsPerBlock / 32);
+        p.slots = 1;
+    } else {
+        p.group = 256;
+        int64_t per = ceil_div(p.total, max_ctas);
+        per = ceil_div(per, kThreadsPerBlock) * kThreadsPerBlock;      // whole rows of threads
+        p.per = per;
+        p.grid = (int)ceil_div(p.total, per);
+        p.slots = (int)(ceil_div(p.nvec, per) + 1);
+    }
     return p;
 }
 
-// Workspace layout (bytes):  [plane counters: planes x int32][sample counters: N x int32]
-//                            [done counter: 64 B][partials: planes x kMaxSplitsUsed x float4]
-// Sized for the worst plan (scalar fallback has the most vectors per plane).
+// Workspace layout (bytes):  [plane tickets: planes x u64][sample tickets: N x u64]
+//                            [done counter: 256 B][partials: planes x slots_bound x float4]
+// slots_bound covers every plan make_plan() can produce for this shape:
+//   slots = ceil(nvec/per) + 1  with  per >= total/kMaxGrid  =>  slots <= kMaxGrid/planes + 2.
 struct Workspace {
-    size_t plane_counters, sample_counters, done_counter, partials, total;
+    size_t plane_tickets, sample_tickets, done_counter, partials, total;
+    int slots_bound;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 inline Workspace workspace_layout(int N, int C, int64_t M, int dtype) {
+    (void)M; (void)dtype;
     Workspace w;
     const int64_t planes = (int64_t)N * C;
-    int smax = 1;
-    for (int align = 1; align <= 32; align *= 2) {
-        const int s = make_plan(N, C, M, dtype, align).splits;
-        if (s > smax) smax = s;
-    }
+    w.slots_bound = (int)(kMaxGrid / planes + 2);
     size_t off = 0;
-    w.plane_counters = off; off = align_up(off + planes * sizeof(int32_t), 256);
-    w.sample_counters = off; off = align_up(off + (size_t)N * sizeof(int32_t), 256);
+    w.plane_tickets = off; off = align_up(off + planes * sizeof(uint64_t), 256);
+    w.sample_tickets = off; off = align_up(off + (size_t)N * sizeof(uint64_t), 256);
     w.done_counter = off; off += 256;
-    w.partials = off; off = align_up(off + (size_t)planes * smax * 16, 256);
+    w.partials = off; off = align_up(off + (size_t)planes * w.slots_bound * 16, 256);
     w.total = off;
     return w;
 }

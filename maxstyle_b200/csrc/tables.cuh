@@ -33,29 +33,27 @@ tables_kernel(const float* __restrict__ mu_all, const float* __restrict__ sig_al
     const int c = blockIdx.x;
     const bool mix = flags & 1, no_noise = flags & 2, compute_std = flags & 4;
     float gs = 0.f, bs = 0.f;
-    if (!no_noise) {
-        if (compute_std) {
-            float s_sig = 0.f, s_mu = 0.f;
-            for (int n = threadIdx.x; n < n_global; n += kTableThreads) {
-                s_sig += sig_all[(int64_t)n * ld + c];
-                s_mu += mu_all[(int64_t)n * ld + c];
-            }
-            const float mean_sig = block_sum_128(s_sig, red) / (float)n_global;
-            const float mean_mu = block_sum_128(s_mu, red) / (float)n_global;
-            float q_sig = 0.f, q_mu = 0.f;
-            for (int n = threadIdx.x; n < n_global; n += kTableThreads) {
-                const float ds = sig_all[(int64_t)n * ld + c] - mean_sig;
-                const float dm = mu_all[(int64_t)n * ld + c] - mean_mu;
-                q_sig = fmaf(ds, ds, q_sig);
-                q_mu = fmaf(dm, dm, q_mu);
-            }
-            gs = sqrtf(block_sum_128(q_sig, red) / (float)(n_global - 1));
-            bs = sqrtf(block_sum_128(q_mu, red) / (float)(n_global - 1));
-            if (threadIdx.x == 0) { gamma_std[c] = gs; beta_std[c] = bs; }
-        } else {
-            gs = gamma_std[c];
-            bs = beta_std[c];
+    if (compute_std && gamma_std != nullptr) {     // the reference fills the cache whatever no_noise says (:165-168)
+        float s_sig = 0.f, s_mu = 0.f;
+        for (int n = threadIdx.x; n < n_global; n += kTableThreads) {
+            s_sig += sig_all[(int64_t)n * ld + c];
+            s_mu += mu_all[(int64_t)n * ld + c];
         }
+        const float mean_sig = block_sum_128(s_sig, red) / (float)n_global;
+        const float mean_mu = block_sum_128(s_mu, red) / (float)n_global;
+        float q_sig = 0.f, q_mu = 0.f;
+        for (int n = threadIdx.x; n < n_global; n += kTableThreads) {
+            const float ds = sig_all[(int64_t)n * ld + c] - mean_sig;
+            const float dm = mu_all[(int64_t)n * ld + c] - mean_mu;
+            q_sig = fmaf(ds, ds, q_sig);
+            q_mu = fmaf(dm, dm, q_mu);
+        }
+        gs = sqrtf(block_sum_128(q_sig, red) / (float)(n_global - 1));
+        bs = sqrtf(block_sum_128(q_mu, red) / (float)(n_global - 1));
+        if (threadIdx.x == 0) { gamma_std[c] = gs; beta_std[c] = bs; }
+    } else if (!no_noise) {
+        gs = gamma_std[c];
+        bs = beta_std[c];
     }
     for (int n = threadIdx.x; n < n_local; n += kTableThreads) {
         const int64_t row = (int64_t)row_offset + n;

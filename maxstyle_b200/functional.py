@@ -16,6 +16,22 @@ from . import _lib as L
 _DTYPES = {torch.float32: L.F32, torch.bfloat16: L.BF16}
 
 
+def _default_sweeps():
+    """Sweep flags of the three streaming kernels (include/maxstyle_b200.h).  The apply kernel walks x
+    in the opposite direction to the statistics kernel and the backward walks it forward again, so each
+    kernel starts on the part of x its predecessor left in L2.  MAXSTYLE_SWEEP="stats,apply,bwd"
+    (three integers) overrides them for experiments."""
+    import os
+    env = os.environ.get("MAXSTYLE_SWEEP")
+    if env:
+        a, b, c = (int(v) for v in env.split(","))
+        return a, b, c
+    return L.SWEEP_X_KEEP, L.SWEEP_REVERSE | L.SWEEP_X_KEEP, L.SWEEP_X_STREAM
+
+
+SWEEP_STATS, SWEEP_APPLY, SWEEP_BWD = _default_sweeps()
+
+
 class _LaunchCounter:
     """Counts kernels of libmaxstyle_b200.so enqueued through this module (bench.py's gpu_launches)."""
     kernels = 0
@@ -103,7 +119,8 @@ def table_ld(mu_all: torch.Tensor) -> int:
     return int(mu_all.stride(0))
 
 
-def instance_stats(x: torch.Tensor, eps: float, workspace: torch.Tensor, mu_all=None, sig_all=None, row_offset: int = 0):
+def instance_stats(x: torch.Tensor, eps: float, workspace: torch.Tensor, mu_all=None, sig_all=None, row_offset: int = 0,
+                   sweep: Optional[int] = None):
     """Kernel 1.  Returns (mu_all, sig_all) with rows [row_offset, row_offset+N) filled."""
     _require_cuda(x, "x")
     n, c, h, w = x.shape
@@ -111,8 +128,8 @@ def instance_stats(x: torch.Tensor, eps: float, workspace: torch.Tensor, mu_all=
         mu_all = torch.empty(n, c, dtype=torch.float32, device=x.device)
         sig_all = torch.empty(n, c, dtype=torch.float32, device=x.device)
     rc = L.get_lib().maxstyle_stats(x.data_ptr(), mu_all.data_ptr(), sig_all.data_ptr(), table_ld(mu_all), row_offset,
-                                    n, c, h, w, dtype_code(x), L.NCHW, eps, workspace.data_ptr(), workspace.numel(),
-                                    _stream())
+                                    n, c, h, w, dtype_code(x), L.NCHW, eps, SWEEP_STATS if sweep is None else sweep,
+                                    workspace.data_ptr(), workspace.numel(), _stream())
     L.check(rc, "maxstyle_stats")
     launches.kernels += 1
     return mu_all, sig_all
@@ -132,11 +149,12 @@ def style_tables(mu_all, sig_all, row_offset: int, n_local: int, perm_dev, lmda,
     return scale, shift
 
 
-def style_apply(x, mu_all, row_offset: int, scale, shift, out=None):
+def style_apply(x, mu_all, row_offset: int, scale, shift, out=None, sweep: Optional[int] = None):
     n, c, h, w = x.shape
     y = torch.empty_like(x, memory_format=torch.contiguous_format) if out is None else out
     rc = L.get_lib().maxstyle_apply(x.data_ptr(), y.data_ptr(), mu_all.data_ptr(), table_ld(mu_all), row_offset,
-                                    scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), L.NCHW, _stream())
+                                    scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), L.NCHW,
+                                    SWEEP_APPLY if sweep is None else sweep, _stream())
     L.check(rc, "maxstyle_apply")
     launches.kernels += 1
     return y
@@ -154,7 +172,7 @@ def forward_raw(x, perm_dev, lmda, gamma_noise, beta_noise, gamma_std, beta_std,
     rc = L.get_lib().maxstyle_fwd(x.data_ptr(), y.data_ptr(), mu.data_ptr(), sig.data_ptr(), _ptr(perm_dev), _ptr(lmda),
                                   _ptr(gamma_noise), _ptr(beta_noise), _ptr(gamma_std), _ptr(beta_std),
                                   scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), L.NCHW, flags, eps,
-                                  workspace.data_ptr(), workspace.numel(), _stream())
+                                  SWEEP_STATS, SWEEP_APPLY, workspace.data_ptr(), workspace.numel(), _stream())
     L.check(rc, "maxstyle_fwd")
     launches.kernels += 3            # stats + tables + apply
     return y, mu, sig, scale, shift
@@ -182,7 +200,7 @@ def backward_raw(dy, x, mu_all, sig_all, row_offset: int, scale, perm_dev, lmda,
                                   table_ld(mu_all), mu_all.shape[0], row_offset, scale.data_ptr(), _ptr(perm_dev), _ptr(lmda),
                                   _ptr(gamma_std), _ptr(beta_std), flags, _ptr(dg), _ptr(db), _ptr(dl),
                                   C.byref(step) if step is not None else None,
-                                  n, c, h, w, dtype_code(x), L.NCHW, workspace.data_ptr(), workspace.numel(), _stream())
+                                  n, c, h, w, dtype_code(x), L.NCHW, SWEEP_BWD, workspace.data_ptr(), workspace.numel(), _stream())
     L.check(rc, "maxstyle_bwd")
     launches.kernels += 1
     return dx, dg, db, dl

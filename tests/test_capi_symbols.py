@@ -38,8 +38,8 @@ def test_library_is_sm100a_only_and_uses_256bit_accesses():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out and not re.search(r"sm_(?!100a)\d+", out), out
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    # Blackwell-only forms: 256-bit global loads/stores carrying an L2 eviction priority
-    assert re.search(r"LDG\.E\.NA\.EFL2\.256", sass) and re.search(r"STG\.E\.NA\.EFL2\.256", sass)
+    # Blackwell-only forms: 256-bit global loads/stores carrying a run-time L2 cache policy
+    assert re.search(r"LDG\.E\.NA\.ENL2\.256", sass) and re.search(r"STG\.E\.NA\.ENL2\.256", sass)
 
 
 def test_host_entry_points(lib):
@@ -56,11 +56,11 @@ def test_host_entry_points(lib):
 
 def test_bad_arguments_return_codes_not_crashes(lib):
     # null pointers are rejected before any CUDA call
-    assert lib.maxstyle_stats(None, None, None, 4, 0, 4, 4, 8, 8, 0, 0, 1e-6, None, 0, None) == 1
-    assert lib.maxstyle_apply(None, None, None, 4, 0, None, None, 4, 4, 8, 8, 0, 0, None) == 1
+    assert lib.maxstyle_stats(None, None, None, 4, 0, 4, 4, 8, 8, 0, 0, 1e-6, 0, None, 0, None) == 1
+    assert lib.maxstyle_apply(None, None, None, 4, 0, None, None, 4, 4, 8, 8, 0, 0, 0, None) == 1
     assert lib.maxstyle_tables(None, None, 4, 4, 0, 4, 4, None, None, None, None, None, None, 0, None, None, None) == 1
-    assert lib.maxstyle_stats(None, None, None, 4, 0, 4, 4, 8, 8, 3, 0, 1e-6, None, 0, None) == 2   # dtype
-    assert lib.maxstyle_stats(None, None, None, 4, 0, 4, 4, 1, 1, 0, 0, 1e-6, None, 0, None) == 1   # M < 2
+    assert lib.maxstyle_stats(None, None, None, 4, 0, 4, 4, 8, 8, 3, 0, 1e-6, 0, None, 0, None) == 2   # dtype
+    assert lib.maxstyle_stats(None, None, None, 4, 0, 4, 4, 1, 1, 0, 0, 1e-6, 0, None, 0, None) == 1   # M < 2
 
 
 def test_step_struct_layout_matches_header():

@@ -1,0 +1,20 @@
+"""Host-side exhaustive check of the flat-sweep work decomposition (csrc/plan.h + the piece/batch
+iterators of csrc/kernels_nchw.cuh): tests/host/plan_check.cu is compiled for the host and run."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="nvcc not available")
+def test_partition_covers_every_vector_exactly_once(tmp_path):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "plan_check")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "host", "plan_check.cu")],
+                   check=True, capture_output=True)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert "0 failures" in res.stdout

@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""Per-kernel timings through the C ABI (CUDA events on the launching stream) + host overhead of the
+eager module path.  Development tool; bench.py is the contract benchmark.
+
+    python tools/kernel_bench.py [--shape N,C,H,W] [--dtype f32|bf16] [--iters 30] [--sweeps "2,3,4;0,0,0"]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="20,64,224,224")
+    ap.add_argument("--dtype", default="f32")
+    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--sweeps", default="2,3,4;0,0,0;2,3,0;0,1,0;2,2,4")
+    ap.add_argument("--host", action="store_true", help="also measure host overhead of the module path")
+    args = ap.parse_args()
+    from maxstyle_b200 import functional as F, _lib as L, MaxStyle, FusedStyleOptimizer
+    n, c, h, w = (int(v) for v in args.shape.split(","))
+    dt = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    es = 4 if args.dtype == "f32" else 2
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    x = (torch.randn(n, c, h, w, device=dev) * 1.5 + 0.25).to(dt)
+    dy = torch.randn(n, c, h, w, device=dev).to(dt)
+    y = torch.empty_like(x); dx = torch.empty_like(x)
+    E = x.numel()
+    layer = MaxStyle(n, c, p=1.0)
+    ws = F.new_workspace(n, c, h, w, F.dtype_code(x), dev)
+    perm = layer.perm.to(dev)
+    gs = torch.empty(c, device=dev); bs = torch.empty(c, device=dev)
+    tabs = torch.empty(4, n, c, device=dev)
+    mu, sig, scale, shift = tabs[0], tabs[1], tabs[2], tabs[3]
+    lm, gn, bn = layer.lmda.detach(), layer.gamma_noise.detach(), layer.beta_noise.detach()
+    flags = L.FLAG_MIX_STYLE | L.FLAG_COMPUTE_BATCH_STD
+    peak = 6553.9
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+
+    def run(sw, iters):
+        s_st, s_ap, s_bw = sw
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(iters)]
+        for i in range(iters):
+            ev[i][0].record()
+            F.instance_stats(x, 1e-6, ws, mu, sig, 0, sweep=s_st)
+            ev[i][1].record()
+            F.style_tables(mu, sig, 0, n, perm, lm, gn, bn, gs, bs, flags, scale, shift)
+            ev[i][2].record()
+            F.style_apply(x, mu, 0, scale, shift, out=y, sweep=s_ap)
+            ev[i][3].record()
+            F.SWEEP_BWD = s_bw
+            F.backward_raw(dy, x, mu, sig, 0, scale, perm, lm, gs, bs, flags & 3, ws, dx_out=dx,
+                           grads_out=(tabs[2].new_empty(n, c), tabs[2].new_empty(n, c), tabs[2].new_empty(n)))
+            ev[i][4].record()
+        torch.cuda.synchronize()
+        def med(a, b):
+            v = sorted(ev[i][a].elapsed_time(ev[i][b]) for i in range(iters // 3, iters))
+            return v[len(v) // 2]
+        return med(0, 1), med(1, 2), med(2, 3), med(3, 4), med(0, 4)
+
+    for sw in args.sweeps.split(";"):
+        sw = tuple(int(v) for v in sw.split(","))
+        run(sw, 5)
+        st, tb, ap, bw, tot = run(sw, args.iters)
+        gb = lambda k, ms: k * E * es / (ms * 1e-3) / 1e9
+        print(json.dumps({"shape": [n, c, h, w], "dtype": args.dtype, "sweeps": sw,
+                          "stats_us": round(st * 1e3, 1), "tables_us": round(tb * 1e3, 1), "apply_us": round(ap * 1e3, 1),
+                          "bwd_us": round(bw * 1e3, 1), "step_us": round(tot * 1e3, 1),
+                          "stats_GBps": round(gb(1, st)), "apply_GBps": round(gb(2, ap)), "bwd_GBps": round(gb(3, bw)),
+                          "step_frac_5E": round(gb(5, tot) / peak, 3)}))
+
+    if args.host:
+        # host overhead: tiny tensors, so the GPU is never the bottleneck; wall clock per eager step
+        nn_, cc_ = 8, 16
+        small = MaxStyle(nn_, cc_, p=1.0)
+        opt = FusedStyleOptimizer([small], lr=0.1)
+        xs = torch.randn(nn_, cc_, 32, 32, device=dev, requires_grad=True)
+        dys = torch.randn(nn_, cc_, 32, 32, device=dev)
+        for _ in range(20):
+            small(xs).backward(dys)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        k = 300
+        for _ in range(k):
+            xs.grad = None
+            small(xs).backward(dys)
+            opt.step()
+        torch.cuda.synchronize()
+        per = (time.perf_counter() - t0) / k
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for _ in range(k):
+                small(xs)
+        torch.cuda.synchronize()
+        per_f = (time.perf_counter() - t0) / k
+        print(json.dumps({"host_us_per_eager_step": round(per * 1e6, 1), "host_us_per_forward_nograd": round(per_f * 1e6, 1)}))
+        import cProfile, pstats, io
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(200):
+            xs.grad = None
+            small(xs).backward(dys)
+            opt.step()
+        torch.cuda.synchronize()
+        pr.disable()
+        sio = io.StringIO()
+        pstats.Stats(pr, stream=sio).sort_stats("cumulative").print_stats(25)
+        print(sio.getvalue()[:5000])
+
+
+if __name__ == "__main__":
+    main()
