@@ -71,53 +71,60 @@ def ncu_traffic():
 # clocks: nvidia-smi sampled DURING the timed region
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML from a background thread while the timed region
+    runs (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; a polling
+    nvidia-smi subprocess stalls kernel launches while it starts up, NVML calls from this process do not)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.proc = None
-        self.path = None
+    def __init__(self, gpu_index: int, period_s: float = 0.02):
+        self.gpu, self.period = gpu_index, period_s
+        self.samples, self.thread, self.stop_flag, self.err = [], None, False, None
 
     def start(self):
+        import threading
         try:
-            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
-            os.close(fd)
-            self.out = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=self.out, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.out.close()
-        sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        with open(self.path) as f:
-            for line in f:
-                parts = [p.strip() for p in line.split(",")]
-                if len(parts) < 9:
-                    continue
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if visible:
                 try:
-                    sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
-                except ValueError:
-                    continue
-                for nm, val in zip(names, parts[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-        os.unlink(self.path)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                    idx = int(visible.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:           # noqa: BLE001
+            self.err = f"nvml unavailable: {e}"
+            return
+
+        def loop():
+            while not self.stop_flag:
+                try:
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    self.samples.append((time.perf_counter(), sm, rs, pw))
+                except Exception as e:   # noqa: BLE001
+                    self.err = str(e)
+                    return
+                time.sleep(self.period)
+
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def stop(self, t0=None, t1=None) -> dict:
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        inside = [s for s in self.samples if (t0 is None or s[0] >= t0) and (t1 is None or s[0] <= t1)] or self.samples
+        reasons = sorted(k for k, bit in self.REASONS.items() if any(s[2] & bit for s in inside))
+        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": float(self.max_sm),
+                "power_w_max": max(s[3] for s in inside), "samples": len(inside), "reasons": reasons,
+                "source": "NVML (clocks.sm / clocks_event_reasons), sampled every 20 ms from the start of the timed region "
+                          "to the end of the load-hold loop that follows it"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -157,7 +164,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=5)
@@ -217,29 +224,47 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    t_region0 = time.perf_counter()
     # ---- timed region: exactly K steps, CUDA events on the launching (current) stream ------
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    # Two events per step bracket the dominant kernel (the backward sweep) for the roofline line; set
+    # BENCH_INNER_EVENTS=0 to time the K steps with the begin/end events only.
+    inner = os.environ.get("BENCH_INNER_EVENTS", "1") != "0"
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = F.launches.kernels
     barrier()
     e_begin.record()
-    for i in range(K):
-        ev[i][0].record()
-        y = layer(x)
-        ev[i][1].record()
-        x.grad = None
-        y.backward(dy)
-        ev[i][2].record()
-        opt.step()
+    if inner:
+        for i in range(K):
+            y = layer(x)
+            x.grad = None
+            ev[i][0].record()
+            y.backward(dy)
+            ev[i][1].record()
+            opt.step()
+    else:
+        for i in range(K):
+            y = layer(x)
+            x.grad = None
+            y.backward(dy)
+            opt.step()
     e_end.record()
     barrier()
     launches = F.launches.kernels - launches0
     total_ms = e_begin.elapsed_time(e_end)
-    fwd_ms = statistics.fmean(ev[i][0].elapsed_time(ev[i][1]) for i in range(K))
-    bwd_ms = statistics.fmean(ev[i][1].elapsed_time(ev[i][2]) for i in range(K))
+    if not inner:                        # separate instrumented pass (not part of `value`)
+        for i in range(K):
+            y = layer(x)
+            x.grad = None
+            ev[i][0].record()
+            y.backward(dy)
+            ev[i][1].record()
+        barrier()
+    bwd_ms = statistics.fmean(ev[i][0].elapsed_time(ev[i][1]) for i in range(K))
+    fwd_ms = total_ms / K - bwd_ms
     # keep the same load running (untimed) long enough for nvidia-smi's 100 ms sampling to see it
     t_hold = time.perf_counter()
-    while rank == 0 and world == 1 and time.perf_counter() - t_hold < 1.5:
+    while rank == 0 and world == 1 and time.perf_counter() - t_hold < 1.0:
         for _ in range(20):
             step()
         torch.cuda.synchronize()
@@ -247,7 +272,7 @@ def main():
         for _ in range(200):
             step()
         barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_region0, time.perf_counter()) if rank == 0 else None
 
     t = torch.tensor([total_ms, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -289,17 +289,23 @@ struct StepCoef {
     float one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps, lr;
 };
 
+// 1 - beta^t without cancellation: -expm1(t * log1p(-(1 - beta))), in fp32 (relative error ~1e-7;
+// torch evaluates the same quantities in double on the host and rounds the results to fp32).
+__device__ __forceinline__ float one_minus_pow(float one_minus_beta, int t) {
+    return -expm1f((float)t * log1pf(-one_minus_beta));
+}
+
 __device__ __forceinline__ StepCoef step_coef(const StepArgs& s) {
     StepCoef c{};
     if (s.mode == 1) {
         const int t = s.step_dev ? (*(volatile int*)s.step_dev + 1) : s.t;
-        const double bc1 = 1.0 - pow(s.beta1, (double)t);
-        const double bc2 = 1.0 - pow(s.beta2, (double)t);
         c.one_minus_b1 = (float)(1.0 - s.beta1);
         c.b2 = (float)s.beta2;
         c.one_minus_b2 = (float)(1.0 - s.beta2);
-        c.step_size = (float)(s.lr / bc1);
-        c.bc2_sqrt = (float)sqrt(bc2);
+        const float bc1 = one_minus_pow(c.one_minus_b1, t);
+        const float bc2 = one_minus_pow(c.one_minus_b2, t);
+        c.step_size = (float)s.lr / bc1;
+        c.bc2_sqrt = sqrtf(bc2);
         c.eps = (float)s.eps;
     }
     c.lr = (float)s.lr;
@@ -349,11 +355,9 @@ struct BwdTables {
 template <int G>
 __device__ __forceinline__ void bwd_finalize_sample(int n, const BwdTables& tb, const StepArgs& st, const Sweep& g,
                                                     const float4* partials, int* done_counter, Scratch& scratch) {
-    // CTA mode: one warp per channel, its lanes over the CTAs that shared the plane;
-    // warp mode: one lane per channel (every plane has exactly one partial).
-    constexpr int kSub = G > 32 ? 32 : 1;                  // lanes cooperating on one channel
+    // One thread per channel: every channel's chain of dependent loads (partials -> tables -> Adam state)
+    // runs in parallel with the others; the partials of a shared plane are summed in slot order.
     const int t = GroupIdx<G>::lane();
-    const int sub = t / kSub, sl = t % kSub;
     const int C = tb.C;
     const int64_t row = (int64_t)tb.row_offset + n;
     const bool mix = tb.flags & 1, no_noise = tb.flags & 2;
@@ -361,33 +365,27 @@ __device__ __forceinline__ void bwd_finalize_sample(int n, const BwdTables& tb, 
     const StepCoef coef = step_coef(st);
     const int ld = tb.ld;
     float lam_acc = 0.f, unused = 0.f;
-    for (int c0 = 0; c0 < C; c0 += G / kSub) {
-        const int c = c0 + sub;
-        float s1 = 0.f, s2 = 0.f;
+    for (int c = t; c < C; c += G) {
         const int64_t plane = (int64_t)n * C + c;
-        if (c < C) {
-            int count = 1;
-            if constexpr (G > 32) count = plane_share(g, plane).count;
-            const float4* slot = partials + plane * g.slots;
-            for (int k = sl; k < count; k += kSub) {
-                const float4 p = __ldcg(&slot[k]);
-                s1 += p.x;
-                s2 += p.y;
-            }
+        int count = 1;
+        if constexpr (G > 32) count = plane_share(g, plane).count;
+        const float4* slot = partials + plane * g.slots;
+        float s1 = 0.f, s2 = 0.f;
+        for (int k = 0; k < count; ++k) {
+            const float4 p = __ldcg(&slot[k]);
+            s1 += p.x;
+            s2 += p.y;
         }
-        if constexpr (kSub > 1) { s1 = warp_sum(s1); s2 = warp_sum(s2); }
-        if (c < C && sl == 0) {
-            const float sg = tb.sig_all[row * ld + c], m = tb.mu_all[row * ld + c];
-            const float dA = s2 / sg, dB = s1;
-            const float gg = no_noise ? 0.f : dA * tb.gamma_std[c];
-            const float gb = no_noise ? 0.f : dB * tb.beta_std[c];
-            if (tb.d_gamma) tb.d_gamma[plane] = gg;
-            if (tb.d_beta) tb.d_beta[plane] = gb;
-            if (mix) lam_acc += dA * (tb.sig_all[prow * ld + c] - sg) + dB * (tb.mu_all[prow * ld + c] - m);
-            if (st.mode != 0 && st.update_noise) {
-                step_update(st.mode, st.maximize, coef, gg, st.gamma_noise + plane, st.gamma_m + plane, st.gamma_v + plane);
-                step_update(st.mode, st.maximize, coef, gb, st.beta_noise + plane, st.beta_m + plane, st.beta_v + plane);
-            }
+        const float sg = tb.sig_all[row * ld + c], m = tb.mu_all[row * ld + c];
+        const float dA = s2 / sg, dB = s1;
+        const float gg = no_noise ? 0.f : dA * tb.gamma_std[c];
+        const float gb = no_noise ? 0.f : dB * tb.beta_std[c];
+        if (tb.d_gamma) tb.d_gamma[plane] = gg;
+        if (tb.d_beta) tb.d_beta[plane] = gb;
+        if (mix) lam_acc += dA * (tb.sig_all[prow * ld + c] - sg) + dB * (tb.mu_all[prow * ld + c] - m);
+        if (st.mode != 0 && st.update_noise) {
+            step_update(st.mode, st.maximize, coef, gg, st.gamma_noise + plane, st.gamma_m + plane, st.gamma_v + plane);
+            step_update(st.mode, st.maximize, coef, gb, st.beta_noise + plane, st.beta_m + plane, st.beta_v + plane);
         }
     }
     group_sum2<G>(lam_acc, unused, scratch);

@@ -80,6 +80,55 @@ def main():
                           "stats_GBps": round(gb(1, st)), "apply_GBps": round(gb(2, ap)), "bwd_GBps": round(gb(3, bw)),
                           "step_frac_5E": round(gb(5, tot) / peak, 3)}))
 
+    # ---- where does the eager module path lose time against the raw sequence? ----------------------
+    def timed(fn, iters=40, warm=8):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+
+    F.SWEEP_STATS, F.SWEEP_APPLY, F.SWEEP_BWD = (int(v) for v in args.sweeps.split(";")[0].split(","))
+    big = MaxStyle(n, c, p=1.0)
+    xr = x.detach().clone().requires_grad_(True)
+    res = {}
+
+    def module_step():
+        xr.grad = None
+        big(xr).backward(dy)
+    res["module_torch_grads_us"] = round(timed(module_step), 1)
+    opt = FusedStyleOptimizer([big], lr=0.1)
+    res["module_fused_adam_us"] = round(timed(module_step), 1)
+    st_struct = big._fused_step.struct(big.gamma_noise, big.beta_noise, big.lmda)
+    gstd, bstd = big.gamma_std.view(-1), big.beta_std.view(-1)
+
+    def raw_step(step=None, fresh=False):
+        yy = torch.empty_like(x) if fresh else y
+        dd = torch.empty_like(x) if fresh else dx
+        F.forward_raw(x, perm, big.lmda, big.gamma_noise, big.beta_noise, gstd, bstd, flags & 3, 1e-6, ws, out=yy, tables=tabs)
+        F.backward_raw(dy, x, mu, sig, 0, scale, perm, big.lmda, gstd, bstd, flags & 3, ws, dx_out=dd,
+                       need_noise_grad=step is None, need_mix_grad=step is None, step=step)
+    res["raw_nograd_step_us"] = round(timed(lambda: raw_step(None)), 1)
+    res["raw_fused_adam_us"] = round(timed(lambda: raw_step(st_struct)), 1)
+    res["raw_fused_adam_fresh_alloc_us"] = round(timed(lambda: raw_step(st_struct, True)), 1)
+    # the same raw sequence replayed from a CUDA graph
+    gph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        raw_step(st_struct)
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(gph):
+        raw_step(st_struct)
+    res["graph_fused_adam_us"] = round(timed(gph.replay), 1)
+    res["roofline_5E_us"] = round(5 * E * es / (peak * 1e9) * 1e6, 1)
+    print(json.dumps(res))
+
     if args.host:
         # host overhead: tiny tensors, so the GPU is never the bottleneck; wall clock per eager step
         nn_, cc_ = 8, 16
