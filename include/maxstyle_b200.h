@@ -47,7 +47,8 @@ enum {
     MAXSTYLE_ERR_UNSUPPORTED = 2,  /* dtype / layout / shape this build has no kernel for    */
     MAXSTYLE_ERR_WORKSPACE = 3,    /* workspace missing, too small or misaligned             */
     MAXSTYLE_ERR_CUDA = 4,         /* cudaGetLastError() after a launch was not cudaSuccess  */
-    MAXSTYLE_ERR_NO_DEVICE = 5     /* no sm_100 device / wrong architecture                  */
+    MAXSTYLE_ERR_NO_DEVICE = 5,    /* no sm_100 device / wrong architecture                  */
+    MAXSTYLE_ERR_TIMEOUT = 6       /* maxstyle_workspace_status: a device-side wait gave up  */
 };
 
 enum { MAXSTYLE_F32 = 0, MAXSTYLE_BF16 = 1 };           /* element type of x / y / dy / dx      */
@@ -72,7 +73,8 @@ enum {
     MAXSTYLE_SWEEP_REVERSE = 1,    /* walk each CTA's slice from its high end                         */
     MAXSTYLE_SWEEP_X_KEEP = 2,     /* loads of x: L2 evict-last (a later kernel re-reads x)           */
     MAXSTYLE_SWEEP_X_STREAM = 4,   /* loads of x: L2 evict-first (last use of x)                      */
-    MAXSTYLE_SWEEP_IO_NORMAL = 8   /* y / dy / dx: default L2 policy instead of evict-first            */
+    MAXSTYLE_SWEEP_IO_NORMAL = 8,  /* y / dy / dx: default L2 policy instead of evict-first            */
+    MAXSTYLE_SWEEP_NO_FUSED = 16   /* maxstyle_fwd (stats_sweep): always take the two-pass path        */
 };
 
 /* optimiser step fused into the backward epilogue (north_star item 4) */
@@ -131,14 +133,29 @@ int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, in
                    const float* shift, int N, int C, int H, int W, int dtype, int layout, int sweep,
                    maxstyle_stream_t stream);
 
-/* Whole forward on one GPU (N_global == N): stats -> tables -> apply, one call.
- * Replaces MaxStyle.forward's active path (maxstyle.py:157-185). */
+/* Whole forward on one GPU (N_global == N), one call.  Replaces MaxStyle.forward's active path
+ * (maxstyle.py:157-185).  Two implementations, same results up to summation order:
+ *  - fused (default when the shape qualifies: planes are 16-byte multiples of at least 8-16 KB, 2 <= N <= 1024,
+ *    one channel of x is at most 40 MB): ONE persistent kernel working through an ordered queue of
+ *    statistics and apply items, channel-major, with the apply items a ~32 MB window behind the
+ *    statistics items, so the second read of x comes out of L2 -- HBM sees x once and y once;
+ *  - two-pass: maxstyle_stats -> maxstyle_tables -> maxstyle_apply (x read from HBM twice). */
 int maxstyle_fwd(const void* x, void* y, float* mu, float* sig,
                  const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
                  float* gamma_std, float* beta_std, float* scale, float* shift,
                  int N, int C, int H, int W, int dtype, int layout, int flags, float eps,
                  int stats_sweep, int apply_sweep,
                  void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
+
+/* Number of kernels maxstyle_fwd launches for this shape on the current device: 1 (fused), 3 (two-pass:
+ * stats, tables, apply), 0 for an unsupported shape.  Assumes 16-byte aligned x and y. */
+int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int stats_sweep);
+
+/* Debug / test helper, the only entry point that synchronises: waits for `stream` and returns
+ * MAXSTYLE_ERR_TIMEOUT if a device-side wait of the fused forward gave up since the workspace
+ * was zero-filled (cannot happen unless the co-residency guarantee of the cooperative launch is broken). */
+int maxstyle_workspace_status(const void* workspace, size_t workspace_bytes, int N, int C, int H, int W, int dtype, int layout,
+                              maxstyle_stream_t stream);
 
 /* Kernel 3 -- backward (replaces the autograd graph of maxstyle.py:157-185).
  * One sweep over dy and x:  dx = dy*scale (skipped when dx == NULL),  dA = sum dy*(x-mu)/sig,

@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
 FLAG_MIX_STYLE, FLAG_NO_NOISE, FLAG_COMPUTE_BATCH_STD = 1, 2, 4
 STEP_NONE, STEP_ADAM, STEP_SIGN = 0, 1, 2
-SWEEP_REVERSE, SWEEP_X_KEEP, SWEEP_X_STREAM, SWEEP_IO_NORMAL = 1, 2, 4, 8
+SWEEP_REVERSE, SWEEP_X_KEEP, SWEEP_X_STREAM, SWEEP_IO_NORMAL, SWEEP_NO_FUSED = 1, 2, 4, 8, 16
 
 _f32p = C.c_void_p      # device pointers travel as plain addresses
 _vp = C.c_void_p
@@ -51,6 +51,8 @@ SIGNATURES = {
     "maxstyle_fwd": (C.c_int, [_vp, _vp, _f32p, _f32p, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
+    "maxstyle_fwd_kernels": (C.c_int, [C.c_int] * 7),
+    "maxstyle_workspace_status": (C.c_int, [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "maxstyle_bwd": (C.c_int, [_vp, _vp, _vp, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _vp, _f32p, _f32p, _f32p,
                                C.c_int, _f32p, _f32p, _f32p, C.POINTER(StepStruct),
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),

@@ -2,8 +2,10 @@
 #include "../../include/maxstyle_b200.h"
 #include "kernels_nchw.cuh"
 #include "tables.cuh"
+#include "fused_fwd.cuh"
 
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 namespace {
 
@@ -132,6 +134,47 @@ int check_step(const maxstyle_step_t* s) {
     return MAXSTYLE_OK;
 }
 
+// ---- fused forward ------------------------------------------------------------------------------------
+struct FwdCall {
+    const void* x; void* y; float *mu, *sig; const int64_t* perm; const float *lmda, *gamma_noise, *beta_noise;
+    float *gamma_std, *beta_std, *scale, *shift; int N, C; int64_t M; int dtype, flags; float eps;
+    char* ws; cudaStream_t stream;
+};
+
+template <typename T, int VEC>
+void launch_fused(const FwdCall& f, const FusedArgs& a, int grid) {
+    fwd_fused_kernel<T, VEC, vpt_for<VEC, 1>()><<<grid, kThreads, 0, f.stream>>>(static_cast<const T*>(f.x), static_cast<T*>(f.y), a);
+}
+
+// Returns MAXSTYLE_OK after launching, -1 when this problem does not qualify (the caller then takes the
+// two-pass path), or an error code.
+int try_fused_fwd(const FwdCall& f, const Workspace& w, int sms) {
+    const FusedPlan fp = make_fused_plan(f.N, f.C, f.M, f.dtype, common_align(f.x, f.y));
+    if (!fp.ok) return -1;
+    FusedArgs a;
+    a.N = f.N; a.C = f.C; a.M = f.M;
+    a.nvec = fp.nvec; a.pieces = fp.pieces; a.piece_vecs = fp.piece_vecs; a.items_per_channel = fp.items_per_channel;
+    a.window = fp.window; a.total_items = fp.total_items;
+    a.flags = f.flags; a.eps = f.eps;
+    a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
+    a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
+    a.gamma_std = f.gamma_std; a.beta_std = f.beta_std;
+    a.partials = reinterpret_cast<float4*>(f.ws + w.res_partials);
+    unsigned int* fl = reinterpret_cast<unsigned int*>(f.ws + w.res_flags);
+    a.arrived = fl; a.ready = fl + f.C;
+    a.error = reinterpret_cast<int*>(f.ws + w.res_error);
+    a.queue = reinterpret_cast<unsigned long long*>(f.ws + w.res_error + 8);
+    a.done = reinterpret_cast<unsigned int*>(f.ws + w.res_error + 16);
+    int64_t cap = (int64_t)sms * kBlocksPerSM;
+    const int grid = (int)(fp.total_items < cap ? fp.total_items : cap);
+    if (f.dtype == MAXSTYLE_F32) {
+        if (fp.vec == 8) launch_fused<float, 8>(f, a, grid); else launch_fused<float, 4>(f, a, grid);
+    } else {
+        if (fp.vec == 16) launch_fused<__nv_bfloat16, 16>(f, a, grid); else launch_fused<__nv_bfloat16, 8>(f, a, grid);
+    }
+    return check_launch();
+}
+
 }  // namespace
 
 extern "C" {
@@ -146,6 +189,7 @@ const char* maxstyle_strerror(int code) {
         case MAXSTYLE_ERR_WORKSPACE: return "workspace missing, too small or not 256-byte aligned";
         case MAXSTYLE_ERR_CUDA: return "CUDA launch error";
         case MAXSTYLE_ERR_NO_DEVICE: return "no usable CUDA device";
+        case MAXSTYLE_ERR_TIMEOUT: return "a device-side wait of the fused forward timed out; its results are invalid";
         default: return "unknown error code";
     }
 }
@@ -207,12 +251,51 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
                  const float* gamma_noise, const float* beta_noise, float* gamma_std, float* beta_std, float* scale,
                  float* shift, int N, int C, int H, int W, int dtype, int layout, int flags, float eps, int stats_sweep,
                  int apply_sweep, void* workspace, size_t workspace_bytes, maxstyle_stream_t stream) {
-    int rc = maxstyle_stats(x, mu, sig, C, 0, N, C, H, W, dtype, layout, eps, stats_sweep, workspace, workspace_bytes, stream);
+    int rc = check_shape(N, C, H, W, dtype, layout);
+    if (rc) return rc;
+    if (!x || !y || !mu || !sig || !scale || !shift) return MAXSTYLE_ERR_BAD_ARG;
+    if ((flags & MAXSTYLE_MIX_STYLE) && (!perm || !lmda)) return MAXSTYLE_ERR_BAD_ARG;
+    if (!(flags & MAXSTYLE_NO_NOISE) && (!gamma_noise || !beta_noise || !gamma_std || !beta_std)) return MAXSTYLE_ERR_BAD_ARG;
+    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_FUSED) && (gamma_std && beta_std)) {
+        // x read from HBM once: ordered statistics/apply items with the window between them held in L2 (fused_fwd.cuh)
+        const int64_t M = (int64_t)H * W;
+        const Workspace w = workspace_layout(N, C, M, dtype);
+        if ((rc = check_workspace(workspace, workspace_bytes, w))) return rc;
+        const int sms = sm_count();
+        if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+        FwdCall f{x, y, mu, sig, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, M, dtype, flags, eps,
+                  static_cast<char*>(workspace), static_cast<cudaStream_t>(stream)};
+        rc = try_fused_fwd(f, w, sms);
+        if (rc >= 0) return rc;
+    }
+    rc = maxstyle_stats(x, mu, sig, C, 0, N, C, H, W, dtype, layout, eps, stats_sweep, workspace, workspace_bytes, stream);
     if (rc) return rc;
     rc = maxstyle_tables(mu, sig, C, N, 0, N, C, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, flags, scale, shift,
                          stream);
     if (rc) return rc;
     return maxstyle_apply(x, y, mu, C, 0, scale, shift, N, C, H, W, dtype, layout, apply_sweep, stream);
+}
+
+int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int stats_sweep) {
+    if (check_shape(N, C, H, W, dtype, layout) != MAXSTYLE_OK) return 0;
+    if (stats_sweep & MAXSTYLE_SWEEP_NO_FUSED) return 3;
+    return make_fused_plan(N, C, (int64_t)H * W, dtype, 32).ok ? 1 : 3;
+}
+
+int maxstyle_workspace_status(const void* workspace, size_t workspace_bytes, int N, int C, int H, int W, int dtype, int layout,
+                              maxstyle_stream_t stream) {
+    const int rc = check_shape(N, C, H, W, dtype, layout);
+    if (rc) return rc;
+    const Workspace w = workspace_layout(N, C, (int64_t)H * W, dtype);
+    if (workspace == nullptr || workspace_bytes < w.total) return MAXSTYLE_ERR_WORKSPACE;
+    int flag = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (cudaMemcpyAsync(&flag, static_cast<const char*>(workspace) + w.res_error, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+        cudaGetLastError();
+        return MAXSTYLE_ERR_CUDA;
+    }
+    return flag ? MAXSTYLE_ERR_TIMEOUT : MAXSTYLE_OK;
 }
 
 int maxstyle_bwd(const void* dy, const void* x, void* dx, const float* mu_all, const float* sig_all, int table_ld, int N_global,

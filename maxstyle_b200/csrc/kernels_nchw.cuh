@@ -24,6 +24,26 @@ struct TableRef {
     }
 };
 
+// The style arithmetic of maxstyle.py:172-185 for one (n,c): returns scale = A/sig and shift = B.
+// Shared by tables_kernel and the fused forward so the two forward paths agree to the last bit.
+__device__ __forceinline__ void style_coeffs(float sg, float m, float sg_partner, float mu_partner, bool mix, bool no_noise,
+                                             float lmda_raw, float gamma_noise, float beta_noise, float gs, float bs,
+                                             float& scale, float& shift) {
+    float sg_mix = sg, mu_mix = m;
+    if (mix) {
+        const float l = fminf(fmaxf(lmda_raw, 0.f), 1.f);
+        sg_mix = sg * (1.f - l) + sg_partner * l;
+        mu_mix = m * (1.f - l) + mu_partner * l;
+    }
+    float A = sg_mix, B = mu_mix;
+    if (!no_noise) {
+        A = sg_mix + gamma_noise * gs;
+        B = mu_mix + beta_noise * bs;
+    }
+    scale = A / sg;
+    shift = B;
+}
+
 // Geometry of one sweep (device copy of Plan + per-call options).
 struct Sweep {
     int64_t M;        // elements per plane

@@ -68,19 +68,61 @@ inline Plan make_plan(int N, int C, int64_t M, int dtype, int align, int sms) {
     return p;
 }
 
+// ---- fused forward (fused_fwd.cuh): ordered queue of statistics / apply items, channel-major --------
+constexpr int kFusedStreamThreads = kThreadsPerBlock - 32;   // 7 streaming warps + 1 control warp per CTA
+constexpr int kFusedMaxN = 1024;                             // rows a finalising warp keeps in shared memory
+constexpr int64_t kFusedPieceBytes = 64 * 1024;              // target size of one item
+constexpr int64_t kFusedWindowBytes = 32ll << 20;            // x kept in L2 between statistics and apply
+constexpr int64_t kFusedMaxChannelBytes = 40ll << 20;        // beyond this one channel does not fit the window
+
+struct FusedPlan {
+    bool ok;
+    int vec, vpt, nvec, pieces, piece_vecs, items_per_channel, window;
+    int64_t total_items;
+};
+
+// vector loads a thread keeps in flight for one tensor (same rule as the streaming kernels)
+inline int vpt_one_tensor(int vec) { const int v = 32 / vec; return v < 1 ? 1 : (v > 4 ? 4 : v); }
+
+inline FusedPlan make_fused_plan(int N, int C, int64_t M, int dtype, int align) {
+    FusedPlan f{};
+    const int es = elem_size(dtype);
+    if (align >= 32 && (M * es) % 32 == 0) f.vec = 32 / es;
+    else if (align >= 16 && (M * es) % 16 == 0) f.vec = 16 / es;
+    else return f;                                            // scalar planes: two-pass path
+    const int64_t nvec = M / f.vec;
+    const int64_t channel_bytes = (int64_t)N * M * es;
+    if (nvec < 512 || nvec > 0x7fffffff || N < 2 || N > kFusedMaxN || channel_bytes > kFusedMaxChannelBytes) return f;
+    f.nvec = (int)nvec;
+    f.vpt = vpt_one_tensor(f.vec);
+    const int64_t step = (int64_t)kFusedStreamThreads * f.vpt;
+    int64_t piece = kFusedPieceBytes / ((int64_t)f.vec * es) / step * step;
+    if (piece < step) piece = step;
+    f.piece_vecs = (int)piece;
+    f.pieces = (int)ceil_div(nvec, piece);
+    f.items_per_channel = N * f.pieces;
+    int64_t d = kFusedWindowBytes / channel_bytes;
+    if (d < 1) d = 1;
+    if (d > C) d = C;
+    f.window = (int)d;
+    f.total_items = 2ll * C * f.items_per_channel;
+    f.ok = true;
+    return f;
+}
+
 // Workspace layout (bytes):  [plane tickets: planes x u64][sample tickets: N x u64]
 //                            [done counter: 256 B][partials: planes x slots_bound x float4]
+//                            [fused forward: error flag + queue + done 256 B][arrived | ready: 2 x C x u32][item partials]
 // slots_bound covers every plan make_plan() can produce for this shape:
 //   slots = ceil(nvec/per) + 1  with  per >= total/kMaxGrid  =>  slots <= kMaxGrid/planes + 2.
 struct Workspace {
-    size_t plane_tickets, sample_tickets, done_counter, partials, total;
+    size_t plane_tickets, sample_tickets, done_counter, partials, res_error, res_flags, res_partials, total;
     int slots_bound;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 inline Workspace workspace_layout(int N, int C, int64_t M, int dtype) {
-    (void)M; (void)dtype;
     Workspace w;
     const int64_t planes = (int64_t)N * C;
     w.slots_bound = (int)(kMaxGrid / planes + 2);
@@ -89,6 +131,14 @@ inline Workspace workspace_layout(int N, int C, int64_t M, int dtype) {
     w.sample_tickets = off; off = align_up(off + (size_t)N * sizeof(uint64_t), 256);
     w.done_counter = off; off += 256;
     w.partials = off; off = align_up(off + (size_t)planes * w.slots_bound * 16, 256);
+    int64_t items = 0;                                       // the plan depends on the pointers' alignment: take the larger
+    for (int align = 16; align <= 32; align *= 2) {
+        const FusedPlan fp = make_fused_plan(N, C, M, dtype, align);
+        if (fp.ok && (int64_t)C * fp.items_per_channel > items) items = (int64_t)C * fp.items_per_channel;
+    }
+    w.res_error = off; off += 256;                           // int error @0, u64 queue @8, u32 done @16
+    w.res_flags = off; off = align_up(off + (size_t)2 * C * sizeof(uint32_t), 256);
+    w.res_partials = off; off = align_up(off + (size_t)items * 16, 256);
     w.total = off;
     return w;
 }

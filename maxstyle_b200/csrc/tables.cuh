@@ -58,20 +58,13 @@ tables_kernel(const float* __restrict__ mu_all, const float* __restrict__ sig_al
     for (int n = threadIdx.x; n < n_local; n += kTableThreads) {
         const int64_t row = (int64_t)row_offset + n;
         const float sg = sig_all[row * ld + c], m = mu_all[row * ld + c];
-        float sg_mix = sg, mu_mix = m;
-        if (mix) {
-            const float l = fminf(fmaxf(lmda[n], 0.f), 1.f);
-            const int64_t pr = perm[row];
-            sg_mix = sg * (1.f - l) + sig_all[pr * ld + c] * l;
-            mu_mix = m * (1.f - l) + mu_all[pr * ld + c] * l;
-        }
-        float A = sg_mix, B = mu_mix;
-        if (!no_noise) {
-            A = sg_mix + gamma_noise[(int64_t)n * C + c] * gs;
-            B = mu_mix + beta_noise[(int64_t)n * C + c] * bs;
-        }
-        scale[(int64_t)n * C + c] = A / sg;
-        shift[(int64_t)n * C + c] = B;
+        const int64_t pr = mix ? perm[row] : row;
+        float sc, sh;
+        style_coeffs(sg, m, sig_all[pr * ld + c], mu_all[pr * ld + c], mix, no_noise, mix ? lmda[n] : 0.f,
+                     no_noise ? 0.f : gamma_noise[(int64_t)n * C + c], no_noise ? 0.f : beta_noise[(int64_t)n * C + c], gs, bs,
+                     sc, sh);
+        scale[(int64_t)n * C + c] = sc;
+        shift[(int64_t)n * C + c] = sh;
     }
 }
 

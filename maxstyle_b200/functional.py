@@ -65,6 +65,22 @@ def workspace_bytes(n: int, c: int, h: int, w: int, dtype: int, layout: int = L.
     return int(L.get_lib().maxstyle_workspace_bytes(n, c, h, w, dtype, layout))
 
 
+_FWD_KERNELS = {}
+
+
+def fwd_kernel_count(n: int, c: int, h: int, w: int, dtype: int) -> int:
+    key = (n, c, h, w, dtype, SWEEP_STATS)
+    if key not in _FWD_KERNELS:
+        _FWD_KERNELS[key] = int(L.get_lib().maxstyle_fwd_kernels(n, c, h, w, dtype, L.NCHW, SWEEP_STATS))
+    return _FWD_KERNELS[key]
+
+
+def workspace_status(workspace: torch.Tensor, n: int, c: int, h: int, w: int, dtype: int) -> None:
+    """Synchronises; raises if a device-side wait of the fused forward timed out (debug / tests)."""
+    rc = L.get_lib().maxstyle_workspace_status(workspace.data_ptr(), workspace.numel(), n, c, h, w, dtype, L.NCHW, _stream())
+    L.check(rc, "maxstyle_workspace_status")
+
+
 def new_workspace(n: int, c: int, h: int, w: int, dtype: int, device, layout: int = L.NCHW) -> torch.Tensor:
     """Zero-filled scratch (the library keeps it zeroed between calls)."""
     nbytes = workspace_bytes(n, c, h, w, dtype, layout)
@@ -174,7 +190,7 @@ def forward_raw(x, perm_dev, lmda, gamma_noise, beta_noise, gamma_std, beta_std,
                                   scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), L.NCHW, flags, eps,
                                   SWEEP_STATS, SWEEP_APPLY, workspace.data_ptr(), workspace.numel(), _stream())
     L.check(rc, "maxstyle_fwd")
-    launches.kernels += 3            # stats + tables + apply
+    launches.kernels += fwd_kernel_count(n, c, h, w, dtype_code(x))   # 1 (fused) or 3 (stats + tables + apply)
     return y, mu, sig, scale, shift
 
 

@@ -406,3 +406,64 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmaxstyle_b200.so")
     with pytest.raises(_lib.MaxStyleLibraryError, match="no fallback"):
         _lib.get_lib()
+
+
+FUSED_SHAPES = [
+    (20, 64, 224, 224, torch.float32),   # config 1: 4 pieces per plane, window of 8 channels
+    (20, 16, 96, 96, torch.float32),     # config-2 layer 3: one piece per plane, window = all channels
+    (20, 1, 224, 224, torch.float32),    # C = 1: every apply item waits for the whole statistics phase
+    (3, 2, 160, 160, torch.float32),
+    (2, 3, 130, 130, torch.float32),     # 67600-byte planes: 16-byte vectors, ragged last piece
+    (32, 16, 192, 192, torch.float32),   # config 3 per-GPU shape
+    (6, 8, 128, 128, torch.bfloat16),
+    (40, 5, 72, 72, torch.float32),      # N > 32: the finalising warp loops over rows
+]
+
+
+@pytest.mark.parametrize("shape", FUSED_SHAPES)
+def test_fused_forward_matches_two_pass_and_oracle(shape):
+    """maxstyle_fwd's single-kernel fused path (ordered statistics/apply queue, x read from HBM once) against
+    the two-pass path and the float64 oracle; the workspace flags are left clean for the next call."""
+    from maxstyle_b200 import functional as F, _lib as L
+    n, c, h, w, dt = shape
+    torch.manual_seed(n * 7 + c)
+    layer = make_layer(n, c)
+    x_np = make_input(11 + n + c + h, (n, c, h, w))
+    x = n2t(x_np, dt)
+    code = F.dtype_code(x)
+    assert L.get_lib().maxstyle_fwd_kernels(n, c, h, w, code, L.NCHW, 0) == 1, "shape should qualify for the fused path"
+    ws = F.new_workspace(n, c, h, w, code, x.device)
+    perm = layer.perm.to(x.device)
+    flags = L.FLAG_MIX_STYLE | L.FLAG_COMPUTE_BATCH_STD
+    outs = {}
+    for name, sweep in (("fused", 0), ("two_pass", L.SWEEP_NO_FUSED), ("fused_again", 0)):
+        gs = torch.zeros(c, device=x.device); bs = torch.zeros(c, device=x.device)
+        old = F.SWEEP_STATS
+        F.SWEEP_STATS = sweep
+        try:
+            y, mu, sig, scale, shift = F.forward_raw(x, perm, layer.lmda.detach(), layer.gamma_noise.detach(),
+                                                     layer.beta_noise.detach(), gs, bs, flags, 1e-6, ws)
+        finally:
+            F.SWEEP_STATS = old
+        F.workspace_status(ws, n, c, h, w, code)
+        outs[name] = [t.clone() for t in (y, mu, sig, scale, shift, gs, bs)]
+    tol = 2.0 ** -8 if dt == torch.bfloat16 else 2e-6
+    for i, nm in enumerate(("y", "mu", "sig", "scale", "shift", "gamma_std", "beta_std")):
+        a, b = t2n(outs["fused"][i]), t2n(outs["two_pass"][i])
+        assert_rel(a, b, tol if nm == "y" else 1e-5, f"{nm}: fused vs two-pass", scale=max(np.abs(b).max(), 1e-3))
+        assert torch.equal(outs["fused"][i], outs["fused_again"][i]), f"{nm}: fused path not deterministic"
+    st = oracle_state(layer.perm.numpy(), t2n(layer.gamma_noise).reshape(n, c), t2n(layer.beta_noise).reshape(n, c),
+                      t2n(layer.lmda).reshape(n), {})
+    y64, cache = O.forward(t2n(x), st, dtype=np.float64)
+    assert_rel(t2n(outs["fused"][0]), y64, tol if dt == torch.bfloat16 else FWD_RTOL, "y fused vs f64 oracle")
+    assert_rel(t2n(outs["fused"][1]), cache.mu, 1e-6, "mu", scale=max(np.abs(cache.mu).max(), 1e-3))
+    assert np.abs(t2n(outs["fused"][2]) / cache.sig - 1).max() < 1e-5
+
+
+def test_fused_forward_declines_what_it_cannot_hold():
+    from maxstyle_b200 import _lib as L
+    lib = L.get_lib()
+    assert lib.maxstyle_fwd_kernels(256, 32, 512, 512, 0, 0, 0) == 3      # config 5: one channel is 256 MB, no L2 window
+    assert lib.maxstyle_fwd_kernels(6, 2, 37, 41, 0, 0, 0) == 3           # planes not a multiple of 16 bytes
+    assert lib.maxstyle_fwd_kernels(64, 8, 28, 28, 0, 0, 0) == 3          # 3 KB planes: warp-per-plane kernels
+    assert lib.maxstyle_fwd_kernels(20, 64, 224, 224, 0, 0, L.SWEEP_NO_FUSED) == 3

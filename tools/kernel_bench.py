@@ -113,6 +113,9 @@ def main():
         F.forward_raw(x, perm, big.lmda, big.gamma_noise, big.beta_noise, gstd, bstd, flags & 3, 1e-6, ws, out=yy, tables=tabs)
         F.backward_raw(dy, x, mu, sig, 0, scale, perm, big.lmda, gstd, bstd, flags & 3, ws, dx_out=dd,
                        need_noise_grad=step is None, need_mix_grad=step is None, step=step)
+    res["fwd_only_us"] = round(timed(lambda: F.forward_raw(x, perm, big.lmda, big.gamma_noise, big.beta_noise, gstd, bstd, flags & 3,
+                                                           1e-6, ws, out=y, tables=tabs)), 1)
+    res["fwd_kernels"] = F.fwd_kernel_count(n, c, h, w, F.dtype_code(x))
     res["raw_nograd_step_us"] = round(timed(lambda: raw_step(None)), 1)
     res["raw_fused_adam_us"] = round(timed(lambda: raw_step(st_struct)), 1)
     res["raw_fused_adam_fresh_alloc_us"] = round(timed(lambda: raw_step(st_struct, True)), 1)
