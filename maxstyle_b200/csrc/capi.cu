@@ -154,7 +154,7 @@ int try_fused_fwd(const FwdCall& f, const Workspace& w, int sms) {
     FusedArgs a;
     a.N = f.N; a.C = f.C; a.M = f.M;
     a.nvec = fp.nvec; a.pieces = fp.pieces; a.piece_vecs = fp.piece_vecs; a.items_per_channel = fp.items_per_channel;
-    a.window = fp.window; a.total_items = fp.total_items;
+    a.window = fp.window; a.chunk = fp.chunk; a.total_items = fp.total_items;
     a.flags = f.flags; a.eps = f.eps;
     a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
     a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
@@ -166,7 +166,8 @@ int try_fused_fwd(const FwdCall& f, const Workspace& w, int sms) {
     a.queue = reinterpret_cast<unsigned long long*>(f.ws + w.res_error + 8);
     a.done = reinterpret_cast<unsigned int*>(f.ws + w.res_error + 16);
     int64_t cap = (int64_t)sms * kBlocksPerSM;
-    const int grid = (int)(fp.total_items < cap ? fp.total_items : cap);
+    const int64_t units = ceil_div(fp.total_items, fp.chunk);
+    const int grid = (int)(units < cap ? units : cap);
     if (f.dtype == MAXSTYLE_F32) {
         if (fp.vec == 8) launch_fused<float, 8>(f, a, grid); else launch_fused<float, 4>(f, a, grid);
     } else {

@@ -33,6 +33,7 @@ struct FusedArgs {
     int piece_vecs;            // vectors per piece (the last piece of a plane may be shorter)
     int items_per_channel;     // N * Kp
     int window;                // D: channels between statistics and apply (<= C)
+    int chunk;                 // consecutive items a CTA takes per ticket (1..kFusedMaxChunk)
     int64_t total_items;       // 2 * C * items_per_channel
     int flags;
     float eps;
@@ -170,9 +171,11 @@ enum { kBarGo0 = 1, kBarGo1 = 2, kBarTot0 = 3, kBarTot1 = 4, kBarRed = 5 };
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+constexpr int kFusedMaxChunk = 4;
+
 struct FusedShared {
-    long long item_id[2];            // ticket of the item with parity p (>= total_items: stop)
-    float4 tot[2];                   // (n, shifted mean, M2, K) of the statistics item with parity p
+    long long item_id[2];            // first item of the unit with parity p (>= total_items: stop)
+    float4 tot[2][kFusedMaxChunk];   // (n, shifted mean, M2, K) of the statistics items of the unit with parity p
     float red_n[kFusedStreamWarps], red_mean[kFusedStreamWarps], red_m2[kFusedStreamWarps];
     int flag;
     float fin_mu[kFusedMaxN], fin_sig[kFusedMaxN];
@@ -204,59 +207,65 @@ fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a) {
 
     if (t >= kFusedStream) {
         // =============================== control warp ===============================
+        // A unit = `chunk` consecutive items taken with one ticket; lane b of this warp looks after item b of it.
         const int lane = t - kFusedStream;
-        // prepare(i): take the ticket of item i, publish it in sh.item_id[i&1]; returns true when the
-        // streamers may start it right away (statistics item, end of queue, or apply item whose channel is ready)
-        auto take = [&](int i) -> long long {
+        const int B = a.chunk;
+        auto take = [&](int u) -> long long {                   // ticket of unit u -> its first item, published in sh.item_id
             long long id = 0;
-            if (lane == 0) { id = (long long)atomicAdd(a.queue, 1ull); sh.item_id[i & 1] = id; }
+            if (lane == 0) { id = (long long)atomicAdd(a.queue, 1ull) * B; sh.item_id[u & 1] = id; }
             return __shfl_sync(0xffffffffu, id, 0);
         };
-        auto channel_ready = [&](long long id, bool block) -> bool {
-            if (id >= a.total_items) return true;
-            const FusedItem it = fused_item(a, id);
-            if (!it.apply) return true;
-            int ok = 0;
-            if (lane == 0) {
-                ok = ld_acquire_u32(&a.ready[it.c]) != 0u;
-                if (!ok && block) {
-                    const long long t0 = clock64();
-                    while (!(ok = ld_acquire_u32(&a.ready[it.c]) != 0u)) {
-                        __nanosleep(64);
-                        if (clock64() - t0 > kFusedSpinLimit) { *a.error = 1; ok = 1; break; }
+        // may the streamers start this unit?  (statistics items: always; apply items: their channel's tables are ready)
+        auto unit_ready = [&](long long first, bool block) -> bool {
+            int ok = 1;
+            const long long id = first + lane;
+            if (lane < B && id < a.total_items) {
+                const FusedItem it = fused_item(a, id);
+                if (it.apply) {
+                    ok = ld_acquire_u32(&a.ready[it.c]) != 0u;
+                    if (!ok && block) {
+                        const long long t0 = clock64();
+                        while (!(ok = ld_acquire_u32(&a.ready[it.c]) != 0u)) {
+                            __nanosleep(64);
+                            if (clock64() - t0 > kFusedSpinLimit) { *a.error = 1; ok = 1; break; }
+                        }
                     }
                 }
             }
-            return __shfl_sync(0xffffffffu, ok, 0) != 0;
+            return __all_sync(0xffffffffu, ok) != 0;
         };
-        auto go = [&](int i) { __syncwarp(); named_arrive((i & 1) ? kBarGo1 : kBarGo0, kAll); };
+        auto go = [&](int u) { __syncwarp(); named_arrive((u & 1) ? kBarGo1 : kBarGo0, kAll); };
 
         long long cur = take(0);
-        channel_ready(cur, true);                               // nothing of this CTA is pending yet: blocking is safe
+        unit_ready(cur, true);                                  // nothing of this CTA is pending yet: blocking is safe
         go(0);
-        for (int i = 0; cur < a.total_items; ++i) {
-            // while the streamers work on item i: ticket (and, if possible, clearance) for item i+1
-            const long long nxt = take(i + 1);
-            const bool early = channel_ready(nxt, false);
-            if (early) go(i + 1);
-            // item i is done: publish its moments, maybe finalise its channel
-            named_sync((i & 1) ? kBarTot1 : kBarTot0, kAll);
-            const FusedItem it = fused_item(a, cur);
-            if (!it.apply) {
-                bool last = false;
-                if (lane == 0) {
-                    a.partials[(int64_t)it.c * a.items_per_channel + it.n * a.pieces + it.k] = sh.tot[i & 1];
+        for (int u = 0; cur < a.total_items; ++u) {
+            // while the streamers work on unit u: ticket (and, if possible, clearance) for unit u+1
+            const long long nxt = take(u + 1);
+            const bool early = unit_ready(nxt, false);
+            if (early) go(u + 1);
+            // unit u is done: publish the moments of its statistics items, finalise the channels they complete
+            named_sync((u & 1) ? kBarTot1 : kBarTot0, kAll);
+            int last = 0, ch = 0;
+            const long long id = cur + lane;
+            if (lane < B && id < a.total_items) {
+                const FusedItem it = fused_item(a, id);
+                if (!it.apply) {
+                    a.partials[(int64_t)it.c * a.items_per_channel + it.n * a.pieces + it.k] = sh.tot[u & 1][lane];
                     __threadfence();
                     last = atomicAdd(&a.arrived[it.c], 1u) == (unsigned int)a.items_per_channel - 1u;
                     if (last) __threadfence();
+                    ch = it.c;
                 }
-                last = __shfl_sync(0xffffffffu, (int)last, 0) != 0;
-                __syncwarp();
-                if (last) fused_finalize_channel(a, it.c, sh.fin_mu, sh.fin_sig);
             }
-            if (!early) {                                       // the next item waits for something that may have been ours
-                channel_ready(nxt, true);
-                go(i + 1);
+            __syncwarp();
+            for (int b = 0; b < B; ++b) {
+                const int lb = __shfl_sync(0xffffffffu, last, b), cb = __shfl_sync(0xffffffffu, ch, b);
+                if (lb) fused_finalize_channel(a, cb, sh.fin_mu, sh.fin_sig);
+            }
+            if (!early) {                                       // the next unit waits for something that may have been ours
+                unit_ready(nxt, true);
+                go(u + 1);
             }
             cur = nxt;
         }
@@ -276,11 +285,12 @@ fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a) {
 
     // =============================== streaming warps ===============================
     const uint64_t pol_keep = make_policy(kPolicyKeep), pol_stream = make_policy(kPolicyStream);
-    for (int i = 0;; ++i) {
-        named_sync((i & 1) ? kBarGo1 : kBarGo0, kAll);
-        const long long id = sh.item_id[i & 1];
-        if (id >= a.total_items) break;
-        const FusedItem it = fused_item(a, id);
+    for (int u = 0;; ++u) {
+        named_sync((u & 1) ? kBarGo1 : kBarGo0, kAll);
+        const long long first = sh.item_id[u & 1];
+        if (first >= a.total_items) break;
+      for (int ib = 0; ib < a.chunk && first + ib < a.total_items; ++ib) {
+        const FusedItem it = fused_item(a, first + ib);
         const int64_t plane = (int64_t)it.n * a.C + it.c;
         Piece pc;
         pc.plane = plane;
@@ -332,7 +342,7 @@ fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a) {
                 }
             }
             const Moments tot = stream_merge(acc, sh);
-            if (t == 0) sh.tot[i & 1] = make_float4(tot.n, tot.mean, tot.m2, K);
+            if (t == 0) sh.tot[u & 1][ib] = make_float4(tot.n, tot.mean, tot.m2, K);
         } else {
             // ---------------- apply: the control warp has seen the channel's ready flag ----------------
             const float m = __ldcg(a.mu + plane), sc = __ldcg(a.scale + plane), shf = __ldcg(a.shift + plane);
@@ -361,7 +371,8 @@ fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a) {
                 }
             }
         }
-        named_arrive((i & 1) ? kBarTot1 : kBarTot0, kAll);       // hand the item back to the control warp
+      }
+        named_arrive((u & 1) ? kBarTot1 : kBarTot0, kAll);       // hand the unit back to the control warp
     }
 }
 

@@ -11,6 +11,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace ms {
 
@@ -77,14 +78,25 @@ constexpr int64_t kFusedMaxChannelBytes = 40ll << 20;        // beyond this one 
 
 struct FusedPlan {
     bool ok;
-    int vec, vpt, nvec, pieces, piece_vecs, items_per_channel, window;
+    int vec, vpt, nvec, pieces, piece_vecs, items_per_channel, window, chunk;
     int64_t total_items;
 };
 
 // vector loads a thread keeps in flight for one tensor (same rule as the streaming kernels)
 inline int vpt_one_tensor(int vec) { const int v = 32 / vec; return v < 1 ? 1 : (v > 4 ? 4 : v); }
 
+// development knobs: MAXSTYLE_FUSED_PIECE_KB / MAXSTYLE_FUSED_WINDOW_MB override the two sizes above
+inline int64_t env_or(const char* name, int64_t dflt, int64_t unit) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const long v = atol(e);
+    return v > 0 ? (int64_t)v * unit : dflt;
+}
+
 inline FusedPlan make_fused_plan(int N, int C, int64_t M, int dtype, int align) {
+    static const int64_t piece_bytes = env_or("MAXSTYLE_FUSED_PIECE_KB", kFusedPieceBytes, 1024);
+    static const int64_t window_bytes = env_or("MAXSTYLE_FUSED_WINDOW_MB", kFusedWindowBytes, 1 << 20);
+    static const int64_t chunk = env_or("MAXSTYLE_FUSED_CHUNK", 1, 1);
     FusedPlan f{};
     const int es = elem_size(dtype);
     if (align >= 32 && (M * es) % 32 == 0) f.vec = 32 / es;
@@ -96,16 +108,17 @@ inline FusedPlan make_fused_plan(int N, int C, int64_t M, int dtype, int align) 
     f.nvec = (int)nvec;
     f.vpt = vpt_one_tensor(f.vec);
     const int64_t step = (int64_t)kFusedStreamThreads * f.vpt;
-    int64_t piece = kFusedPieceBytes / ((int64_t)f.vec * es) / step * step;
+    int64_t piece = piece_bytes / ((int64_t)f.vec * es) / step * step;
     if (piece < step) piece = step;
     f.piece_vecs = (int)piece;
     f.pieces = (int)ceil_div(nvec, piece);
     f.items_per_channel = N * f.pieces;
-    int64_t d = kFusedWindowBytes / channel_bytes;
+    int64_t d = window_bytes / channel_bytes;
     if (d < 1) d = 1;
     if (d > C) d = C;
     f.window = (int)d;
     f.total_items = 2ll * C * f.items_per_channel;
+    f.chunk = (int)(chunk < 1 ? 1 : (chunk > 4 ? 4 : chunk));
     f.ok = true;
     return f;
 }

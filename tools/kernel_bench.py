@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--sweeps", default="2,3,4;0,0,0;2,3,0;0,1,0;2,2,4")
     ap.add_argument("--host", action="store_true", help="also measure host overhead of the module path")
+    ap.add_argument("--fwd-only", action="store_true", help="only time maxstyle_fwd")
     args = ap.parse_args()
     from maxstyle_b200 import functional as F, _lib as L, MaxStyle, FusedStyleOptimizer
     n, c, h, w = (int(v) for v in args.shape.split(","))
@@ -69,6 +70,22 @@ def main():
             return v[len(v) // 2]
         return med(0, 1), med(1, 2), med(2, 3), med(3, 4), med(0, 4)
 
+    if args.fwd_only:
+        F.SWEEP_STATS, F.SWEEP_APPLY, F.SWEEP_BWD = (int(v) for v in args.sweeps.split(";")[0].split(","))
+        for _ in range(5):
+            F.forward_raw(x, perm, lm, gn, bn, gs, bs, flags, 1e-6, ws, out=y, tables=tabs)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.iters):
+            F.forward_raw(x, perm, lm, gn, bn, gs, bs, flags & 3, 1e-6, ws, out=y, tables=tabs)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / args.iters * 1e3
+        print(json.dumps({"shape": [n, c, h, w], "dtype": args.dtype, "fwd_us": round(us, 1), "fwd_GBps_2E": round(2 * E * es / us / 1e3),
+                          "kernels": F.fwd_kernel_count(n, c, h, w, F.dtype_code(x)), "piece_kb": os.environ.get("MAXSTYLE_FUSED_PIECE_KB"),
+                          "window_mb": os.environ.get("MAXSTYLE_FUSED_WINDOW_MB"), "chunk": os.environ.get("MAXSTYLE_FUSED_CHUNK")}))
+        return
     for sw in args.sweeps.split(";"):
         sw = tuple(int(v) for v in sw.split(","))
         run(sw, 5)
