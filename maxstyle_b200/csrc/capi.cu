@@ -3,6 +3,7 @@
 #include "kernels_nchw.cuh"
 #include "tables.cuh"
 #include "fused_fwd.cuh"
+#include "kernels_nhwc.cuh"
 
 #include <cuda_runtime.h>
 #include <cstdlib>
@@ -32,9 +33,15 @@ int check_shape(int N, int C, int H, int W, int dtype, int layout) {
     if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return MAXSTYLE_ERR_BAD_ARG;
     if ((int64_t)H * W < 2) return MAXSTYLE_ERR_BAD_ARG;          // unbiased variance needs M >= 2
     if (dtype != MAXSTYLE_F32 && dtype != MAXSTYLE_BF16) return MAXSTYLE_ERR_UNSUPPORTED;
-    if (layout != MAXSTYLE_NCHW) return MAXSTYLE_ERR_UNSUPPORTED;
+    if (layout != MAXSTYLE_NCHW && layout != MAXSTYLE_NHWC) return MAXSTYLE_ERR_UNSUPPORTED;
+    if (layout == MAXSTYLE_NHWC && C > 1 && !make_plan_nhwc(N, C, (int64_t)H * W, dtype, 32, 148).ok &&
+        !make_plan_nhwc(N, C, (int64_t)H * W, dtype, 1, 148).ok)
+        return MAXSTYLE_ERR_UNSUPPORTED;                        // more than 256 vectors per pixel
     return MAXSTYLE_OK;
 }
+
+// With one channel the two layouts are the same memory: the NCHW kernels take it.
+inline bool is_nhwc(int layout, int C) { return layout == MAXSTYLE_NHWC && C > 1; }
 
 int check_workspace(const void* ws, size_t bytes, const Workspace& w) {
     if (ws == nullptr || bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 255u)) return MAXSTYLE_ERR_WORKSPACE;
@@ -88,6 +95,72 @@ void launch_bwd(const void* dy, const void* x, void* dx, char* ws, const Workspa
         bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), false><<<p.grid, kThreads, 0, s>>>(
             static_cast<const T*>(dy), static_cast<const T*>(x), nullptr, partials, tickets, done, g, tb, st);
 }
+
+// ---- NHWC dispatch on (dtype, vector width) -----------------------------------------------------------
+Sweep sweep_of_nhwc(const PlanNhwc& p, int N, int64_t M, int sweep) {
+    Sweep g;
+    g.M = M; g.nvec = p.nvec; g.planes = N; g.total = p.total; g.per = p.per; g.slots = p.slots;
+    g.reverse = 0;                                              // the NHWC kernels sweep forward only
+    g.in_policy = (sweep & MAXSTYLE_SWEEP_X_KEEP) ? kPolicyKeep : ((sweep & MAXSTYLE_SWEEP_X_STREAM) ? kPolicyStream : kPolicyNormal);
+    g.io_policy = (sweep & MAXSTYLE_SWEEP_IO_NORMAL) ? kPolicyNormal : kPolicyStream;
+    return g;
+}
+
+RowGeom geom_of(const PlanNhwc& p, int C) {
+    RowGeom r;
+    r.C = C; r.cv = p.cv; r.active = p.active;
+    r.shuffle = (p.cv < 32 && 32 % p.cv == 0) ? 1 : 0;
+    return r;
+}
+
+// vectors in flight per thread and tensor: 32 fp32 values' worth of loads for one tensor, 16 per tensor for two
+template <int VEC, int TENSORS> constexpr int vpt_nhwc() {
+    constexpr int v = (TENSORS == 1 ? 32 : 16) / VEC;
+    return v < 1 ? 1 : (v > 4 ? 4 : v);
+}
+
+template <typename T, int VEC>
+void launch_stats_nhwc(const void* x, float* mu, float* sig, TableRef tr, char* ws, const Workspace& w, const PlanNhwc& p, int N,
+                       int64_t M, float eps, int sweep, cudaStream_t s) {
+    stats_nhwc_kernel<T, VEC, vpt_nhwc<VEC, 1>()><<<p.grid, kThreads, 0, s>>>(
+        static_cast<const T*>(x), mu, sig, tr, reinterpret_cast<float4*>(ws + w.partials),
+        reinterpret_cast<unsigned long long*>(ws + w.plane_tickets), sweep_of_nhwc(p, N, M, sweep), geom_of(p, tr.C), eps);
+}
+
+template <typename T, int VEC>
+void launch_apply_nhwc(const void* x, void* y, const float* mu, TableRef tr, const float* scale, const float* shift,
+                       const PlanNhwc& p, int N, int64_t M, int sweep, cudaStream_t s) {
+    apply_nhwc_kernel<T, VEC, vpt_nhwc<VEC, 1>()><<<p.grid, kThreads, 0, s>>>(
+        static_cast<const T*>(x), static_cast<T*>(y), mu, tr, scale, shift, sweep_of_nhwc(p, N, M, sweep), geom_of(p, tr.C));
+}
+
+template <typename T, int VEC>
+void launch_bwd_nhwc(const void* dy, const void* x, void* dx, char* ws, const Workspace& w, const PlanNhwc& p, int N, int64_t M,
+                     const BwdTables& tb, const StepArgs& st, int sweep, cudaStream_t s) {
+    float4* partials = reinterpret_cast<float4*>(ws + w.partials);
+    unsigned long long* tickets = reinterpret_cast<unsigned long long*>(ws + w.sample_tickets);
+    int* done = reinterpret_cast<int*>(ws + w.done_counter);
+    const Sweep g = sweep_of_nhwc(p, N, M, sweep);
+    const RowGeom rg = geom_of(p, tb.C);
+    if (dx)
+        bwd_nhwc_kernel<T, VEC, vpt_nhwc<VEC, 2>(), true><<<p.grid, kThreads, 0, s>>>(
+            static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<T*>(dx), partials, tickets, done, g, rg, tb, st);
+    else
+        bwd_nhwc_kernel<T, VEC, vpt_nhwc<VEC, 2>(), false><<<p.grid, kThreads, 0, s>>>(
+            static_cast<const T*>(dy), static_cast<const T*>(x), nullptr, partials, tickets, done, g, rg, tb, st);
+}
+
+#define MS_DISPATCH_NHWC(FN, dtype, plan, ...)                                                     \
+    do {                                                                                           \
+        if ((dtype) == MAXSTYLE_F32) {                                                             \
+            if ((plan).vec == 8) FN<float, 8>(__VA_ARGS__);                                        \
+            else if ((plan).vec == 4) FN<float, 4>(__VA_ARGS__);                                   \
+            else FN<float, 1>(__VA_ARGS__);                                                        \
+        } else {                                                                                   \
+            if ((plan).vec == 8) FN<__nv_bfloat16, 8>(__VA_ARGS__);                                \
+            else FN<__nv_bfloat16, 1>(__VA_ARGS__);                                                \
+        }                                                                                          \
+    } while (0)
 
 #define MS_DISPATCH_G(FN, T, V, plan, ...)                                                         \
     do {                                                                                           \
@@ -197,7 +270,7 @@ const char* maxstyle_strerror(int code) {
 
 size_t maxstyle_workspace_bytes(int N, int C, int H, int W, int dtype, int layout) {
     if (check_shape(N, C, H, W, dtype, layout) != MAXSTYLE_OK) return 0;
-    return workspace_layout(N, C, (int64_t)H * W, dtype).total;
+    return workspace_layout(N, C, (int64_t)H * W, dtype, is_nhwc(layout, C)).total;
 }
 
 int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, int row_offset, int N, int C, int H, int W,
@@ -207,12 +280,19 @@ int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, i
     if (rc) return rc;
     if (!x || !mu_all || !sig_all || row_offset < 0 || table_ld < C) return MAXSTYLE_ERR_BAD_ARG;
     const int64_t M = (int64_t)H * W;
-    const Workspace w = workspace_layout(N, C, M, dtype);
+    const Workspace w = workspace_layout(N, C, M, dtype, is_nhwc(layout, C));
     if ((rc = check_workspace(workspace, workspace_bytes, w))) return rc;
     const int sms = sm_count();
     if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
-    const Plan p = make_plan(N, C, M, dtype, common_align(x), sms);
     const TableRef tr{C, table_ld, row_offset};
+    if (is_nhwc(layout, C)) {
+        const PlanNhwc pn = make_plan_nhwc(N, C, M, dtype, common_align(x), sms);
+        if (!pn.ok) return MAXSTYLE_ERR_UNSUPPORTED;
+        MS_DISPATCH_NHWC(launch_stats_nhwc, dtype, pn, x, mu_all, sig_all, tr, static_cast<char*>(workspace), w, pn, N, M, eps,
+                         sweep, static_cast<cudaStream_t>(stream));
+        return check_launch();
+    }
+    const Plan p = make_plan(N, C, M, dtype, common_align(x), sms);
     MS_DISPATCH(launch_stats, dtype, p, x, mu_all, sig_all, tr, static_cast<char*>(workspace), w, p, M, eps, sweep,
                 static_cast<cudaStream_t>(stream));
     return check_launch();
@@ -241,8 +321,15 @@ int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, in
     const int sms = sm_count();
     if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
     const int64_t M = (int64_t)H * W;
-    const Plan p = make_plan(N, C, M, dtype, common_align(x, y), sms);
     const TableRef tr{C, table_ld, row_offset};
+    if (is_nhwc(layout, C)) {
+        const PlanNhwc pn = make_plan_nhwc(N, C, M, dtype, common_align(x, y), sms);
+        if (!pn.ok) return MAXSTYLE_ERR_UNSUPPORTED;
+        MS_DISPATCH_NHWC(launch_apply_nhwc, dtype, pn, x, y, mu_all, tr, scale, shift, pn, N, M, sweep,
+                         static_cast<cudaStream_t>(stream));
+        return check_launch();
+    }
+    const Plan p = make_plan(N, C, M, dtype, common_align(x, y), sms);
     MS_DISPATCH(launch_apply, dtype, p, x, y, mu_all, tr, scale, shift, p, M, sweep,
                 static_cast<cudaStream_t>(stream));
     return check_launch();
@@ -257,7 +344,7 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
     if (!x || !y || !mu || !sig || !scale || !shift) return MAXSTYLE_ERR_BAD_ARG;
     if ((flags & MAXSTYLE_MIX_STYLE) && (!perm || !lmda)) return MAXSTYLE_ERR_BAD_ARG;
     if (!(flags & MAXSTYLE_NO_NOISE) && (!gamma_noise || !beta_noise || !gamma_std || !beta_std)) return MAXSTYLE_ERR_BAD_ARG;
-    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_FUSED) && (gamma_std && beta_std)) {
+    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_FUSED) && (gamma_std && beta_std) && !is_nhwc(layout, C)) {
         // x read from HBM once: ordered statistics/apply items with the window between them held in L2 (fused_fwd.cuh)
         const int64_t M = (int64_t)H * W;
         const Workspace w = workspace_layout(N, C, M, dtype);
@@ -279,7 +366,7 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
 
 int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int stats_sweep) {
     if (check_shape(N, C, H, W, dtype, layout) != MAXSTYLE_OK) return 0;
-    if (stats_sweep & MAXSTYLE_SWEEP_NO_FUSED) return 3;
+    if ((stats_sweep & MAXSTYLE_SWEEP_NO_FUSED) || is_nhwc(layout, C)) return 3;
     return make_fused_plan(N, C, (int64_t)H * W, dtype, 32).ok ? 1 : 3;
 }
 
@@ -287,7 +374,7 @@ int maxstyle_workspace_status(const void* workspace, size_t workspace_bytes, int
                               maxstyle_stream_t stream) {
     const int rc = check_shape(N, C, H, W, dtype, layout);
     if (rc) return rc;
-    const Workspace w = workspace_layout(N, C, (int64_t)H * W, dtype);
+    const Workspace w = workspace_layout(N, C, (int64_t)H * W, dtype, is_nhwc(layout, C));
     if (workspace == nullptr || workspace_bytes < w.total) return MAXSTYLE_ERR_WORKSPACE;
     int flag = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -312,16 +399,23 @@ int maxstyle_bwd(const void* dy, const void* x, void* dx, const float* mu_all, c
     if (!(flags & MAXSTYLE_NO_NOISE) && (!gamma_std || !beta_std)) return MAXSTYLE_ERR_BAD_ARG;
     if ((rc = check_step(step))) return rc;
     const int64_t M = (int64_t)H * W;
-    const Workspace w = workspace_layout(N, C, M, dtype);
+    const Workspace w = workspace_layout(N, C, M, dtype, is_nhwc(layout, C));
     if ((rc = check_workspace(workspace, workspace_bytes, w))) return rc;
     const int sms = sm_count();
     if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
-    const Plan p = make_plan(N, C, M, dtype, common_align(dy, x, dx), sms);
     BwdTables tb;
     tb.mu_all = mu_all; tb.sig_all = sig_all; tb.scale = scale; tb.perm = perm; tb.lmda = lmda;
     tb.gamma_std = gamma_std; tb.beta_std = beta_std; tb.d_gamma = d_gamma; tb.d_beta = d_beta; tb.d_lmda = d_lmda;
     tb.row_offset = row_offset; tb.N = N; tb.C = C; tb.flags = flags; tb.ld = table_ld;
     const StepArgs st = to_step_args(step);
+    if (is_nhwc(layout, C)) {
+        const PlanNhwc pn = make_plan_nhwc(N, C, M, dtype, common_align(dy, x, dx), sms);
+        if (!pn.ok) return MAXSTYLE_ERR_UNSUPPORTED;
+        MS_DISPATCH_NHWC(launch_bwd_nhwc, dtype, pn, dy, x, dx, static_cast<char*>(workspace), w, pn, N, M, tb, st, sweep,
+                         static_cast<cudaStream_t>(stream));
+        return check_launch();
+    }
+    const Plan p = make_plan(N, C, M, dtype, common_align(dy, x, dx), sms);
     MS_DISPATCH(launch_bwd, dtype, p, dy, x, dx, static_cast<char*>(workspace), w, p, M, tb, st, sweep,
                 static_cast<cudaStream_t>(stream));
     return check_launch();

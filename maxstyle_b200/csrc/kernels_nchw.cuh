@@ -374,7 +374,10 @@ struct BwdTables {
 
 template <int G>
 __device__ __forceinline__ void bwd_finalize_sample(int n, const BwdTables& tb, const StepArgs& st, const Sweep& g,
-                                                    const float4* partials, int* done_counter, Scratch& scratch) {
+                                                    const float4* partials, int* done_counter, Scratch& scratch,
+                                                    int fixed_count = -1) {
+    // `fixed_count` >= 0: every channel of the sample has that many partials (NHWC: the sample, not the plane, is
+    // what CTAs share); otherwise the count comes from the plane's share of the flat NCHW sweep.
     // One thread per channel: every channel's chain of dependent loads (partials -> tables -> Adam state)
     // runs in parallel with the others; the partials of a shared plane are summed in slot order.
     const int t = GroupIdx<G>::lane();
@@ -388,7 +391,8 @@ __device__ __forceinline__ void bwd_finalize_sample(int n, const BwdTables& tb, 
     for (int c = t; c < C; c += G) {
         const int64_t plane = (int64_t)n * C + c;
         int count = 1;
-        if constexpr (G > 32) count = plane_share(g, plane).count;
+        if (fixed_count >= 0) count = fixed_count;
+        else if constexpr (G > 32) count = plane_share(g, plane).count;
         const float4* slot = partials + plane * g.slots;
         float s1 = 0.f, s2 = 0.f;
         for (int k = 0; k < count; ++k) {

@@ -69,6 +69,48 @@ inline Plan make_plan(int N, int C, int64_t M, int dtype, int align, int sms) {
     return p;
 }
 
+// ---- NHWC (channels-last) feature maps: kernels_nhwc.cuh --------------------------------------------
+// Memory is [N][H*W][C]: a pixel is a row of C contiguous elements = CV vector accesses, a sample is
+// M*CV contiguous vectors.  The tensor is swept as ONE flat space of N*M*CV vectors cut into pieces at
+// SAMPLE boundaries; `active` = floor(256/CV)*CV threads of a CTA stream it, so a thread meets the same
+// VEC channels at every step ((v0 + t + i*active) mod CV is constant) and keeps their statistics in registers.
+constexpr int kBlocksPerSMNhwc = 3;             // 3 x 256 threads per SM: up to 85 registers for the per-channel state
+
+struct PlanNhwc {
+    bool ok;
+    int vec;          // elements per vector access (32 B or 16 B / sizeof(T), or 1)
+    int cv;           // vectors per pixel = C / vec
+    int active;       // streaming threads per CTA: floor(256/cv)*cv
+    int grid;
+    int slots;        // partial-result slots per (sample, channel) = max number of CTAs sharing a sample
+    int64_t nvec;     // vectors per sample = M * cv
+    int64_t total;    // N * nvec
+    int64_t per;      // vectors per CTA (a multiple of `active`)
+};
+
+inline PlanNhwc make_plan_nhwc(int N, int C, int64_t M, int dtype, int align, int sms) {
+    PlanNhwc p{};
+    const int es = elem_size(dtype);
+    // bf16 keeps to 16-byte vectors (8 channels): 16 channels of running statistics per thread do not fit the registers
+    if (dtype == 0 && align >= 32 && ((int64_t)C * es) % 32 == 0) p.vec = 32 / es;
+    else if (align >= 16 && ((int64_t)C * es) % 16 == 0) p.vec = 16 / es;
+    else p.vec = 1;
+    p.cv = C / p.vec;
+    if (p.cv > kThreadsPerBlock) return p;                     // more than 256 vectors per pixel: no kernel
+    p.active = kThreadsPerBlock / p.cv * p.cv;
+    p.nvec = M * p.cv;
+    p.total = (int64_t)N * p.nvec;
+    int64_t max_ctas = (int64_t)sms * kBlocksPerSMNhwc;
+    if (max_ctas > kMaxGrid) max_ctas = kMaxGrid;
+    int64_t per = ceil_div(p.total, max_ctas);
+    per = ceil_div(per, p.active) * p.active;
+    p.per = per;
+    p.grid = (int)ceil_div(p.total, per);
+    p.slots = (int)(ceil_div(p.nvec, per) + 1);
+    p.ok = true;
+    return p;
+}
+
 // ---- fused forward (fused_fwd.cuh): ordered queue of statistics / apply items, channel-major --------
 constexpr int kFusedStreamThreads = kThreadsPerBlock - 32;   // 7 streaming warps + 1 control warp per CTA
 constexpr int kFusedMaxN = 1024;                             // rows a finalising warp keeps in shared memory
@@ -128,6 +170,7 @@ inline FusedPlan make_fused_plan(int N, int C, int64_t M, int dtype, int align) 
 //                            [fused forward: error flag + queue + done 256 B][arrived | ready: 2 x C x u32][item partials]
 // slots_bound covers every plan make_plan() can produce for this shape:
 //   slots = ceil(nvec/per) + 1  with  per >= total/kMaxGrid  =>  slots <= kMaxGrid/planes + 2.
+// NHWC (layout 1): the shared unit is the sample, each CTA publishes C partials for it (make_plan_nhwc).
 struct Workspace {
     size_t plane_tickets, sample_tickets, done_counter, partials, res_error, res_flags, res_partials, total;
     int slots_bound;
@@ -135,7 +178,7 @@ struct Workspace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-inline Workspace workspace_layout(int N, int C, int64_t M, int dtype) {
+inline Workspace workspace_layout(int N, int C, int64_t M, int dtype, int layout = 0) {
     Workspace w;
     const int64_t planes = (int64_t)N * C;
     w.slots_bound = (int)(kMaxGrid / planes + 2);
@@ -143,7 +186,12 @@ inline Workspace workspace_layout(int N, int C, int64_t M, int dtype) {
     w.plane_tickets = off; off = align_up(off + planes * sizeof(uint64_t), 256);
     w.sample_tickets = off; off = align_up(off + (size_t)N * sizeof(uint64_t), 256);
     w.done_counter = off; off += 256;
-    w.partials = off; off = align_up(off + (size_t)planes * w.slots_bound * 16, 256);
+    size_t partial_bytes = (size_t)planes * w.slots_bound * 16;
+    if (layout == 1) {                                       // NHWC: a SAMPLE is shared by <= kMaxGrid/N + 2 CTAs, C partials each
+        const size_t nhwc = (size_t)planes * (size_t)(kMaxGrid / N + 2) * 16;
+        if (nhwc > partial_bytes) partial_bytes = nhwc;
+    }
+    w.partials = off; off = align_up(off + partial_bytes, 256);
     int64_t items = 0;                                       // the plan depends on the pointers' alignment: take the larger
     for (int align = 16; align <= 32; align *= 2) {
         const FusedPlan fp = make_fused_plan(N, C, M, dtype, align);

@@ -119,7 +119,7 @@ class GlobalBatchMaxStyle(MaxStyle):
     def forward(self, x):
         self.data = x
         n, c = x.size(0), x.size(1)
-        plane = x.reshape(n, c, -1).size(2)
+        plane = x.numel() // (n * c) if n * c else 0
         # identity cases; note B <= 1 refers to the GLOBAL batch here
         if (self.rand_p >= self.p) or (not self.mix_style and self.no_noise) or self.global_batch_size <= 1 or plane == 1:
             return x
@@ -134,7 +134,7 @@ class GlobalBatchMaxStyle(MaxStyle):
 class GlobalBatchFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma_noise, beta_noise, lmda, layer):
-        x = x.contiguous()
+        x = F.dense_layout(x)
         n, c = x.shape[0], x.shape[1]
         flags = layer._flags()
         first = layer.gamma_std is None or layer.beta_std is None
@@ -175,9 +175,9 @@ class GlobalBatchFunction(torch.autograd.Function):
         fused = layer._fused_step
         step = fused.struct(layer.gamma_noise, layer.beta_noise, layer.lmda) if fused is not None else None
         keep = fused is None or fused.keep_grads
-        dy = dy.contiguous()
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
+        dy = F._match_layout(dy, x)
         with torch.cuda.device(x.device):
             dx, dg, db, dl = F.backward_raw(dy, x, mu_all, sig_all, layer.row_offset, scale,
                                             layer._perm_device(x.device), lmda, gamma_std, beta_std, ctx.flags,

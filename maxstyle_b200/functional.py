@@ -61,6 +61,34 @@ def dtype_code(t: torch.Tensor) -> int:
         raise RuntimeError(f"maxstyle_b200: unsupported dtype {t.dtype} (float32 and bfloat16 are implemented)")
 
 
+def layout_of(x: torch.Tensor) -> int:
+    """Memory layout code of a dense 4-d feature map.  NCHW-contiguous wins when both hold (C == 1 or H*W == 1)."""
+    if x.is_contiguous():
+        return L.NCHW
+    if x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last):
+        return L.NHWC
+    raise RuntimeError("maxstyle_b200: feature maps must be NCHW-contiguous or channels_last (call dense_layout first)")
+
+
+def dense_layout(x: torch.Tensor) -> torch.Tensor:
+    """x itself when it is NCHW-contiguous or channels_last (the reference accepts both and keeps the format);
+    anything else is made NCHW-contiguous."""
+    if x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)):
+        return x
+    return x.contiguous()
+
+
+def _like(x: torch.Tensor) -> torch.Tensor:
+    """Uninitialised tensor with x's shape, dtype and memory layout."""
+    fmt = torch.contiguous_format if layout_of(x) == L.NCHW else torch.channels_last
+    return torch.empty_like(x, memory_format=fmt)
+
+
+def _match_layout(t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    fmt = torch.contiguous_format if layout_of(like) == L.NCHW else torch.channels_last
+    return t.contiguous(memory_format=fmt)
+
+
 def workspace_bytes(n: int, c: int, h: int, w: int, dtype: int, layout: int = L.NCHW) -> int:
     return int(L.get_lib().maxstyle_workspace_bytes(n, c, h, w, dtype, layout))
 
@@ -68,16 +96,16 @@ def workspace_bytes(n: int, c: int, h: int, w: int, dtype: int, layout: int = L.
 _FWD_KERNELS = {}
 
 
-def fwd_kernel_count(n: int, c: int, h: int, w: int, dtype: int) -> int:
-    key = (n, c, h, w, dtype, SWEEP_STATS)
+def fwd_kernel_count(n: int, c: int, h: int, w: int, dtype: int, layout: int = L.NCHW) -> int:
+    key = (n, c, h, w, dtype, layout, SWEEP_STATS)
     if key not in _FWD_KERNELS:
-        _FWD_KERNELS[key] = int(L.get_lib().maxstyle_fwd_kernels(n, c, h, w, dtype, L.NCHW, SWEEP_STATS))
+        _FWD_KERNELS[key] = int(L.get_lib().maxstyle_fwd_kernels(n, c, h, w, dtype, layout, SWEEP_STATS))
     return _FWD_KERNELS[key]
 
 
-def workspace_status(workspace: torch.Tensor, n: int, c: int, h: int, w: int, dtype: int) -> None:
+def workspace_status(workspace: torch.Tensor, n: int, c: int, h: int, w: int, dtype: int, layout: int = L.NCHW) -> None:
     """Synchronises; raises if a device-side wait of the fused forward timed out (debug / tests)."""
-    rc = L.get_lib().maxstyle_workspace_status(workspace.data_ptr(), workspace.numel(), n, c, h, w, dtype, L.NCHW, _stream())
+    rc = L.get_lib().maxstyle_workspace_status(workspace.data_ptr(), workspace.numel(), n, c, h, w, dtype, layout, _stream())
     L.check(rc, "maxstyle_workspace_status")
 
 
@@ -144,7 +172,7 @@ def instance_stats(x: torch.Tensor, eps: float, workspace: torch.Tensor, mu_all=
         mu_all = torch.empty(n, c, dtype=torch.float32, device=x.device)
         sig_all = torch.empty(n, c, dtype=torch.float32, device=x.device)
     rc = L.get_lib().maxstyle_stats(x.data_ptr(), mu_all.data_ptr(), sig_all.data_ptr(), table_ld(mu_all), row_offset,
-                                    n, c, h, w, dtype_code(x), L.NCHW, eps, SWEEP_STATS if sweep is None else sweep,
+                                    n, c, h, w, dtype_code(x), layout_of(x), eps, SWEEP_STATS if sweep is None else sweep,
                                     workspace.data_ptr(), workspace.numel(), _stream())
     L.check(rc, "maxstyle_stats")
     launches.kernels += 1
@@ -167,9 +195,9 @@ def style_tables(mu_all, sig_all, row_offset: int, n_local: int, perm_dev, lmda,
 
 def style_apply(x, mu_all, row_offset: int, scale, shift, out=None, sweep: Optional[int] = None):
     n, c, h, w = x.shape
-    y = torch.empty_like(x, memory_format=torch.contiguous_format) if out is None else out
+    y = _like(x) if out is None else out
     rc = L.get_lib().maxstyle_apply(x.data_ptr(), y.data_ptr(), mu_all.data_ptr(), table_ld(mu_all), row_offset,
-                                    scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), L.NCHW,
+                                    scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), layout_of(x),
                                     SWEEP_APPLY if sweep is None else sweep, _stream())
     L.check(rc, "maxstyle_apply")
     launches.kernels += 1
@@ -184,13 +212,14 @@ def forward_raw(x, perm_dev, lmda, gamma_noise, beta_noise, gamma_std, beta_std,
     if tables is None:
         tables = torch.empty(4, n, c, dtype=torch.float32, device=x.device)
     mu, sig, scale, shift = tables[0], tables[1], tables[2], tables[3]
-    y = torch.empty_like(x, memory_format=torch.contiguous_format) if out is None else out
+    y = _like(x) if out is None else out
+    layout = layout_of(x)
     rc = L.get_lib().maxstyle_fwd(x.data_ptr(), y.data_ptr(), mu.data_ptr(), sig.data_ptr(), _ptr(perm_dev), _ptr(lmda),
                                   _ptr(gamma_noise), _ptr(beta_noise), _ptr(gamma_std), _ptr(beta_std),
-                                  scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), L.NCHW, flags, eps,
+                                  scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), layout, flags, eps,
                                   SWEEP_STATS, SWEEP_APPLY, workspace.data_ptr(), workspace.numel(), _stream())
     L.check(rc, "maxstyle_fwd")
-    launches.kernels += fwd_kernel_count(n, c, h, w, dtype_code(x))   # 1 (fused) or 3 (stats + tables + apply)
+    launches.kernels += fwd_kernel_count(n, c, h, w, dtype_code(x), layout)   # 1 (fused) or 3 (stats + tables + apply)
     return y, mu, sig, scale, shift
 
 
@@ -202,7 +231,7 @@ def backward_raw(dy, x, mu_all, sig_all, row_offset: int, scale, perm_dev, lmda,
     n, c, h, w = x.shape
     dx = None
     if need_dx:
-        dx = torch.empty_like(x, memory_format=torch.contiguous_format) if dx_out is None else dx_out
+        dx = _like(x) if dx_out is None else dx_out
     dg = db = dl = None
     if grads_out is not None:
         dg, db, dl = grads_out
@@ -216,7 +245,8 @@ def backward_raw(dy, x, mu_all, sig_all, row_offset: int, scale, perm_dev, lmda,
                                   table_ld(mu_all), mu_all.shape[0], row_offset, scale.data_ptr(), _ptr(perm_dev), _ptr(lmda),
                                   _ptr(gamma_std), _ptr(beta_std), flags, _ptr(dg), _ptr(db), _ptr(dl),
                                   C.byref(step) if step is not None else None,
-                                  n, c, h, w, dtype_code(x), L.NCHW, SWEEP_BWD, workspace.data_ptr(), workspace.numel(), _stream())
+                                  n, c, h, w, dtype_code(x), layout_of(x), SWEEP_BWD, workspace.data_ptr(), workspace.numel(),
+                                  _stream())
     L.check(rc, "maxstyle_bwd")
     launches.kernels += 1
     return dx, dg, db, dl
@@ -231,7 +261,7 @@ class MaxStyleFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma_noise, beta_noise, lmda, layer):
-        x = x.contiguous()
+        x = dense_layout(x)                # NCHW or channels_last, as it came (the output keeps the format)
         flags = layer._flags()
         first = layer.gamma_std is None or layer.beta_std is None
         if first:
@@ -263,9 +293,9 @@ class MaxStyleFunction(torch.autograd.Function):
         need_dx, need_g, need_b, need_l = ctx.needs_input_grad[:4]
         fused = layer._fused_step
         step = fused.struct(layer.gamma_noise, layer.beta_noise, layer.lmda) if fused is not None else None
-        dy = dy.contiguous()
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
+        dy = _match_layout(dy, x)
         with torch.cuda.device(x.device):
             dx, dg, db, dl = backward_raw(dy, x, mu, sig, 0, scale, layer._perm_device(x.device), lmda, gamma_std,
                                           beta_std, ctx.flags, layer._workspace_for(x), need_dx=need_dx,

@@ -176,10 +176,11 @@ class MaxStyle(nn.Module):
         return self._perm_dev
 
     def _workspace_for(self, x: torch.Tensor) -> torch.Tensor:
-        key = (x.device, tuple(x.shape), x.dtype)
+        layout = F.layout_of(x)
+        key = (x.device, tuple(x.shape), x.dtype, layout)
         if self._workspace_key != key:
             n, c, h, w = x.shape
-            self._workspace = F.new_workspace(n, c, h, w, F.dtype_code(x), x.device)
+            self._workspace = F.new_workspace(n, c, h, w, F.dtype_code(x), x.device, layout)
             self._workspace_key = key
         return self._workspace
 
@@ -190,7 +191,7 @@ class MaxStyle(nn.Module):
     def forward(self, x):
         self.data = x
         n, c = x.size(0), x.size(1)
-        plane = x.view(n, c, -1).size(2) if x.is_contiguous() else x.reshape(n, c, -1).size(2)
+        plane = x.numel() // (n * c) if n * c else 0     # x.view(B, C, -1).size(2) without touching memory
         # identity cases of the reference (maxstyle.py:146-152): the SAME tensor object comes back
         if (self.rand_p >= self.p) or (not self.mix_style and self.no_noise) or n <= 1 or plane == 1:
             return x

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../../maxstyle_b200/csrc/kernels_nchw.cuh"
+#include "../../maxstyle_b200/csrc/plan.h"
 
 using namespace ms;
 
@@ -73,6 +74,54 @@ void check_case(int N, int C, int64_t M, int dtype, int align, int sms, int reve
     for (int n = 0; n < N; ++n) CHECK(sample[n] == (unsigned long long)C * p.nvec, "sample ticket total");
 }
 
+// NHWC: PlanNhwc + the thread loops of kernels_nhwc.cuh (thread t of a piece starts at v0 + t and steps by
+// `active`, VPT accesses per full step).  Every vector of every sample is visited exactly once, a thread
+// meets one channel vector per piece, the CTAs sharing a sample are plane_share() and fit the slot bounds,
+// and the per-sample tickets add up to the sample's vector count.
+void check_nhwc(int N, int C, int64_t M, int dtype, int align, int sms, int vpt) {
+    const PlanNhwc p = make_plan_nhwc(N, C, M, dtype, align, sms);
+    if (!p.ok) { CHECK(C / p.vec > kThreadsPerBlock, "plan refused although cv = %d", C / p.vec); return; }
+    CHECK(p.cv * p.vec == C && p.active % p.cv == 0 && p.active <= kThreadsPerBlock && p.active > kThreadsPerBlock - p.cv, "geometry cv=%d active=%d", p.cv, p.active);
+    CHECK(p.grid >= 1 && p.grid <= sms * kBlocksPerSMNhwc, "grid %d", p.grid);
+    const Workspace w = workspace_layout(N, C, M, dtype, 1);
+    const Workspace w0 = workspace_layout(N, C, M, dtype, 0);
+    CHECK(w.total >= w0.total, "NHWC workspace smaller than NCHW");
+    CHECK((size_t)N * C * p.slots * 16 <= w.res_error - w.partials, "partials do not fit: slots %d", p.slots);
+    Sweep g{};
+    g.M = M; g.nvec = p.nvec; g.planes = N; g.total = p.total; g.per = p.per; g.slots = p.slots; g.reverse = 0;
+    std::vector<int> cover((size_t)p.total, 0);
+    std::vector<int> touched((size_t)N, 0);
+    std::vector<unsigned long long> ticket((size_t)N, 0);
+    for (int64_t b = 0; b < p.grid; ++b) {
+        PieceIter<kThreads> it(g, b);
+        Piece pc;
+        while (it.next(pc)) {
+            CHECK(pc.plane >= 0 && pc.plane < N && pc.v0 >= 0 && pc.v1 <= p.nvec && pc.v0 < pc.v1, "bad piece");
+            touched[pc.plane]++;
+            ticket[pc.plane] += (unsigned long long)(pc.v1 - pc.v0);
+            const PlaneShare sh = plane_share(g, pc.plane);
+            CHECK(b >= sh.first && b < sh.first + sh.count && sh.count <= p.slots, "sample share");
+            for (int t = 0; t < p.active; ++t) {
+                const int cvv = (int)((pc.v0 + (int64_t)t) % p.cv);
+                int v = pc.v0 + t;
+                for (; v + (vpt - 1) * p.active < pc.v1; v += vpt * p.active)
+                    for (int j = 0; j < vpt; ++j) {
+                        const int idx = v + j * p.active;
+                        CHECK(idx % p.cv == cvv, "channel vector changed");
+                        cover[(size_t)(pc.plane * p.nvec + idx)]++;
+                    }
+                for (; v < pc.v1; v += p.active) { CHECK(v % p.cv == cvv, "channel vector changed (tail)"); cover[(size_t)(pc.plane * p.nvec + v)]++; }
+            }
+        }
+    }
+    for (int64_t i = 0; i < p.total; ++i)
+        if (cover[(size_t)i] != 1) { CHECK(false, "NHWC vector %lld covered %d times (N=%d C=%d M=%lld sms=%d)", (long long)i, cover[(size_t)i], N, C, (long long)M, sms); break; }
+    for (int n = 0; n < N; ++n) {
+        CHECK(touched[n] == plane_share(g, n).count, "sample %d touched %d, share %d", n, touched[n], plane_share(g, n).count);
+        CHECK(ticket[n] == (unsigned long long)p.nvec, "sample ticket total");
+    }
+}
+
 int main() {
     const int shapes[][4] = {{20, 64, 224, 224}, {20, 16, 96, 96}, {20, 1, 224, 224}, {3, 2, 160, 160}, {2, 3, 224, 224}, {4, 5, 56, 56},
                              {20, 1, 64, 64}, {5, 3, 30, 30}, {6, 2, 37, 41}, {2, 2, 512, 512}, {33, 7, 12, 12}, {4, 3, 5, 7}, {2, 1, 8, 8},
@@ -95,6 +144,17 @@ int main() {
                             if (vpt == 1) { check_case<256, 1>(s[0], s[1], M, dtype, align, sms, rev); check_case<32, 1>(s[0], s[1], M, dtype, align, sms, rev); }
                             ++cases;
                         }
+                    }
+    const int nhwc_shapes[][4] = {{20, 64, 56, 56}, {4, 64, 48, 48}, {3, 16, 96, 96}, {2, 8, 64, 64}, {5, 256, 14, 14}, {3, 24, 40, 40},
+                                  {6, 12, 20, 20}, {4, 5, 17, 19}, {2, 320, 9, 9}, {40, 32, 12, 12}, {700, 8, 4, 4}, {2, 2, 300, 300},
+                                  {2, 2048, 3, 3}, {2, 4096, 2, 2}, {1, 3, 2, 1}, {32, 16, 96, 96}};
+    for (auto& s : nhwc_shapes)
+        for (int dtype = 0; dtype < 2; ++dtype)
+            for (int align : {32, 16, 4})
+                for (int sms : {148, 1, 7})
+                    for (int vpt : {1, 2, 4}) {
+                        check_nhwc(s[0], s[1], (int64_t)s[2] * s[3], dtype, align, sms, vpt);
+                        ++cases;
                     }
     printf("%d cases, %d failures\n", cases, failures);
     return failures ? 1 : 0;

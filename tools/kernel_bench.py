@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--sweeps", default="2,3,4;0,0,0;2,3,0;0,1,0;2,2,4")
     ap.add_argument("--host", action="store_true", help="also measure host overhead of the module path")
     ap.add_argument("--fwd-only", action="store_true", help="only time maxstyle_fwd")
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"])
     args = ap.parse_args()
     from maxstyle_b200 import functional as F, _lib as L, MaxStyle, FusedStyleOptimizer
     n, c, h, w = (int(v) for v in args.shape.split(","))
@@ -33,10 +34,12 @@ def main():
     torch.manual_seed(0)
     x = (torch.randn(n, c, h, w, device=dev) * 1.5 + 0.25).to(dt)
     dy = torch.randn(n, c, h, w, device=dev).to(dt)
+    if args.layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last); dy = dy.contiguous(memory_format=torch.channels_last)
     y = torch.empty_like(x); dx = torch.empty_like(x)
     E = x.numel()
     layer = MaxStyle(n, c, p=1.0)
-    ws = F.new_workspace(n, c, h, w, F.dtype_code(x), dev)
+    ws = F.new_workspace(n, c, h, w, F.dtype_code(x), dev, F.layout_of(x))
     perm = layer.perm.to(dev)
     gs = torch.empty(c, device=dev); bs = torch.empty(c, device=dev)
     tabs = torch.empty(4, n, c, device=dev)
@@ -91,7 +94,7 @@ def main():
         run(sw, 5)
         st, tb, ap, bw, tot = run(sw, args.iters)
         gb = lambda k, ms: k * E * es / (ms * 1e-3) / 1e9
-        print(json.dumps({"shape": [n, c, h, w], "dtype": args.dtype, "sweeps": sw,
+        print(json.dumps({"shape": [n, c, h, w], "dtype": args.dtype, "layout": args.layout, "sweeps": sw,
                           "stats_us": round(st * 1e3, 1), "tables_us": round(tb * 1e3, 1), "apply_us": round(ap * 1e3, 1),
                           "bwd_us": round(bw * 1e3, 1), "step_us": round(tot * 1e3, 1),
                           "stats_GBps": round(gb(1, st)), "apply_GBps": round(gb(2, ap)), "bwd_GBps": round(gb(3, bw)),
