@@ -136,7 +136,7 @@ int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, in
 /* Whole forward on one GPU (N_global == N), one call.  Replaces MaxStyle.forward's active path
  * (maxstyle.py:157-185).  Two implementations, same results up to summation order:
  *  - fused (default when the shape qualifies: planes are 16-byte multiples of at least 8-16 KB, 2 <= N <= 1024,
- *    one channel of x is at most 40 MB): ONE persistent kernel working through an ordered queue of
+ *    one channel of x is at most 16 MB, so the L2 window holds >= 2 channels): ONE persistent kernel working through an ordered queue of
  *    statistics and apply items, channel-major, with the apply items a ~32 MB window behind the
  *    statistics items, so the second read of x comes out of L2 -- HBM sees x once and y once;
  *  - two-pass: maxstyle_stats -> maxstyle_tables -> maxstyle_apply (x read from HBM twice). */

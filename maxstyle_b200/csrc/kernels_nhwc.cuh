@@ -124,8 +124,12 @@ stats_nhwc_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
         float mean[VEC], m2[VEC], cnt = 0.f;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) { mean[k] = 0.f; m2[k] = 0.f; }
-        if (t < A) {
+        if (t < A && pc.v0 + t < pc.v1) {
             int v = pc.v0 + t;
+            // The running mean doubles as the shift: deviations are taken from it BEFORE they are summed, so data
+            // whose spread is tiny against its mean loses no digits.  It starts at the thread's first value
+            // (count 0: the first merge has weight 1 and replaces it by that value + the batch's mean deviation).
+            Vec<T, VEC>::load(base + (int64_t)v * VEC, mean, pol);
             for (; v + (VPT - 1) * A < pc.v1; v += VPT * A) {
                 float val[VPT][VEC];
 #pragma unroll
@@ -137,14 +141,13 @@ stats_nhwc_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
                 for (int k = 0; k < VEC; ++k) {
                     float s = 0.f;
 #pragma unroll
-                    for (int j = 0; j < VPT; ++j) s += val[j][k];
-                    const float bm = s * (1.0f / (float)VPT);
+                    for (int j = 0; j < VPT; ++j) { val[j][k] -= mean[k]; s += val[j][k]; }
+                    const float bm = s * (1.0f / (float)VPT);      // batch mean, relative to the running mean
                     float q = 0.f;
 #pragma unroll
                     for (int j = 0; j < VPT; ++j) { const float d = val[j][k] - bm; q = fmaf(d, d, q); }
-                    const float dd = bm - mean[k];
-                    mean[k] = fmaf(dd, w, mean[k]);
-                    m2[k] += fmaf(dd * dd, cw, q);
+                    mean[k] = fmaf(bm, w, mean[k]);
+                    m2[k] += fmaf(bm * bm, cw, q);
                 }
                 cnt = nn;
             }

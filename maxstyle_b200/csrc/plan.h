@@ -116,7 +116,9 @@ constexpr int kFusedStreamThreads = kThreadsPerBlock - 32;   // 7 streaming warp
 constexpr int kFusedMaxN = 1024;                             // rows a finalising warp keeps in shared memory
 constexpr int64_t kFusedPieceBytes = 64 * 1024;              // target size of one item
 constexpr int64_t kFusedWindowBytes = 32ll << 20;            // x kept in L2 between statistics and apply
-constexpr int64_t kFusedMaxChannelBytes = 40ll << 20;        // beyond this one channel does not fit the window
+constexpr int64_t kFusedMaxChannelBytes = 16ll << 20;        // the window must hold >= 2 channels: with one, every apply item
+                                                             // waits for the finaliser of the channel streamed just before it
+                                                             // (measured 2.3x slower than the two-pass path, profiles/r01_sweep.jsonl)
 
 struct FusedPlan {
     bool ok;

@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""R-rank NCCL parity check of GlobalBatchMaxStyle (run under torchrun; one rank per GPU).
+
+Oracle for an R-rank run = the reference on the concatenated global batch: here the
+golden case "mid_16ch" generated from the unmodified reference (tests/golden/fwd_bwd.npz).  Every rank seeds
+like the single-device reference, takes its rows, runs forward + backward (+ a fused Adam step) on its GPU,
+and compares its slab with the golden tensors.  Tolerances: BASELINE.json's 1e-5 forward, 1e-4 gradients,
+perm bit-exact.  Prints one line per rank; exit code != 0 on any mismatch.
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from maxstyle_b200 import GlobalBatchMaxStyle, FusedStyleOptimizer
+    from oracle import maxstyle_oracle as O
+    from oracle.gen_golden import make_input
+
+    man = json.load(open(os.path.join(ROOT, "tests", "golden", "MANIFEST.json")))
+    idx = [m["name"] for m in man["fwd_bwd"]].index("mid_16ch")
+    meta = man["fwd_bwd"][idx]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "fwd_bwd.npz"))
+    pre = f"f{idx}_"
+    n_glob, c, h, w = meta["N"], meta["C"], meta["H"], meta["W"]
+    assert n_glob % world == 0, f"golden batch {n_glob} does not split over {world} ranks"
+    n_loc = n_glob // world
+    off = rank * n_loc
+
+    torch.manual_seed(meta["seed"])
+    layer = GlobalBatchMaxStyle(n_loc, c, p=1.0)
+    assert np.array_equal(layer.perm.numpy(), g[pre + "perm"]), "perm differs from the reference's draw"   # bit-exact
+    # parameters are drawn on the CUDA generator here (the goldens came from the CPU generator): load the recorded rows
+    with torch.no_grad():
+        layer.gamma_noise.copy_(torch.from_numpy(g[pre + "gamma_noise"][off:off + n_loc]).view(n_loc, c, 1, 1))
+        layer.beta_noise.copy_(torch.from_numpy(g[pre + "beta_noise"][off:off + n_loc]).view(n_loc, c, 1, 1))
+        layer.lmda.copy_(torch.from_numpy(g[pre + "lmda"].reshape(-1)[off:off + n_loc]).view(n_loc, 1, 1, 1))
+    x_np = make_input(meta["seed"], (n_glob, c, h, w), meta["kind"])
+    dy_np = np.random.RandomState(meta["seed"] + 5000).standard_normal(size=(n_glob, c, h, w)).astype(np.float32)
+
+    def close(a, b, rtol, name, scale=None):
+        a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+        s = np.abs(b).max() if scale is None else scale
+        err = np.abs(a - b).max()
+        assert err <= rtol * max(s, 1e-30), f"rank {rank} {name}: err {err:.3e} scale {s:.3e} rtol {rtol:g}"
+        return err / max(s, 1e-30)
+
+    errs = {}
+    for fmt, tag in ((torch.contiguous_format, "nchw"), (torch.channels_last, "nhwc")):
+        layer.gamma_std = layer.beta_std = None
+        layer.zero_grad()
+        x = torch.from_numpy(x_np[off:off + n_loc]).to(dev).contiguous(memory_format=fmt).requires_grad_(True)
+        dy = torch.from_numpy(dy_np[off:off + n_loc]).to(dev).contiguous(memory_format=fmt)
+        y = layer(x)
+        y.backward(dy)
+        t2n = lambda t: t.detach().float().cpu().numpy()
+        errs[tag] = dict(
+            y=close(t2n(y), g[pre + "y"][off:off + n_loc], 1e-5, "y"),
+            dx=close(t2n(x.grad), g[pre + "dx"][off:off + n_loc], 1e-4, "dx"),
+            d_gamma=close(t2n(layer.gamma_noise.grad).reshape(n_loc, c), g[pre + "d_gamma_noise"][off:off + n_loc], 1e-4, "d_gamma",
+                          scale=np.abs(g[pre + "d_gamma_noise"]).max()),
+            d_beta=close(t2n(layer.beta_noise.grad).reshape(n_loc, c), g[pre + "d_beta_noise"][off:off + n_loc], 1e-4, "d_beta",
+                         scale=np.abs(g[pre + "d_beta_noise"]).max()),
+            d_lmda=close(t2n(layer.lmda.grad).reshape(-1), g[pre + "d_lmda"].reshape(-1)[off:off + n_loc], 1e-4, "d_lmda",
+                         scale=np.abs(g[pre + "d_lmda"]).max()),
+            gamma_std=close(t2n(layer.gamma_std).reshape(-1), g[pre + "gamma_std"].reshape(-1), 1e-5, "gamma_std",
+                            scale=np.abs(g[pre + "sig"]).max()),
+        )
+    # fused Adam step on the local rows == the oracle's restatement of torch.optim.Adam on those rows
+    before = layer.lmda.detach().cpu().numpy().reshape(-1).copy()
+    grad = layer.lmda.grad.detach().cpu().numpy().reshape(-1).copy()
+    opt = FusedStyleOptimizer([layer], lr=0.1)
+    layer.zero_grad()
+    layer(x).backward(dy)
+    want = O.adam_step(before, grad, O.AdamState(np.zeros(n_loc, np.float32), np.zeros(n_loc, np.float32)))
+    errs["adam_lmda"] = float(np.abs(layer.lmda.detach().cpu().numpy().reshape(-1) - want).max())
+    assert errs["adam_lmda"] < 1e-5, errs
+    dist.barrier()
+    print(f"[dist_parity] rank {rank}/{world} ok", json.dumps({k: (v if isinstance(v, float) else {a: f"{b:.1e}" for a, b in v.items()})
+                                                                for k, v in errs.items()}), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
