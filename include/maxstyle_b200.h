@@ -58,8 +58,10 @@ enum { MAXSTYLE_NCHW = 0, MAXSTYLE_NHWC = 1 };          /* memory layout of x / 
 enum {
     MAXSTYLE_MIX_STYLE = 1,         /* maxstyle.py:172-176 (else :177-179)                     */
     MAXSTYLE_NO_NOISE = 2,          /* maxstyle.py:181-182 (else :183-185)                     */
-    MAXSTYLE_COMPUTE_BATCH_STD = 4  /* first forward: fill gamma_std/beta_std (maxstyle.py:165-168);
+    MAXSTYLE_COMPUTE_BATCH_STD = 4, /* first forward: fill gamma_std/beta_std (maxstyle.py:165-168);
                                        otherwise they are inputs (the reference's cached values) */
+    MAXSTYLE_NO_CLAMP = 8           /* use lmda as given instead of clamp(lmda, 0, 1): the MixStyle layer
+                                       (src/advanced/mixstyle.py:95-96) extrapolates with lmda outside [0,1] */
 };
 
 /* sweep flags -- performance only: how a streaming kernel walks its tensor and what it tells L2.
@@ -74,7 +76,11 @@ enum {
     MAXSTYLE_SWEEP_X_KEEP = 2,     /* loads of x: L2 evict-last (a later kernel re-reads x)           */
     MAXSTYLE_SWEEP_X_STREAM = 4,   /* loads of x: L2 evict-first (last use of x)                      */
     MAXSTYLE_SWEEP_IO_NORMAL = 8,  /* y / dy / dx: default L2 policy instead of evict-first            */
-    MAXSTYLE_SWEEP_NO_FUSED = 16   /* maxstyle_fwd (stats_sweep): always take the two-pass path        */
+    MAXSTYLE_SWEEP_NO_FUSED = 16,  /* maxstyle_fwd (stats_sweep): always take the two-pass path        */
+    MAXSTYLE_SWEEP_NO_RESIDENT = 32, /* maxstyle_fwd (stats_sweep): skip the shared-memory-resident kernel */
+    MAXSTYLE_SWEEP_FORCE_WINDOW = 64, /* maxstyle_fwd (stats_sweep): take the L2-window kernel whenever the
+                                        shape qualifies, even where the two-pass path is faster (tests)   */
+    MAXSTYLE_SWEEP_FORCE_RESIDENT = 128 /* ... likewise for the shared-memory-resident kernel               */
 };
 
 /* optimiser step fused into the backward epilogue (north_star item 4) */
@@ -134,8 +140,13 @@ int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, in
                    maxstyle_stream_t stream);
 
 /* Whole forward on one GPU (N_global == N), one call.  Replaces MaxStyle.forward's active path
- * (maxstyle.py:157-185).  Two implementations, same results up to summation order:
- *  - fused (default when the shape qualifies: planes are 16-byte multiples of at least 8-16 KB, 2 <= N <= 1024,
+ * (maxstyle.py:157-185).  Three implementations, same results up to summation order, tried in this order:
+ *  - resident (16-byte-multiple planes of 16 KB .. ~108 KB so that two CTAs share an SM, tensors >= 64 MB, 2 <= N <=
+ *    number of co-resident CTAs; planes up to ~220 KB with MAXSTYLE_SWEEP_FORCE_RESIDENT): ONE persistent
+ *    kernel; each plane is brought into shared memory once by TMA bulk copies, its moments are taken there, the
+ *    CTA exchanges (mu, sig) with its mixing partner's CTA through global flags, and y is written from shared
+ *    memory while the next plane is already loading -- HBM sees x once and y once, L2 is only passed through;
+ *  - L2 window (when the shape qualifies and it pays: planes >= 64 KB, a channel <= 8 MB: planes are 16-byte multiples of at least 8-16 KB, 2 <= N <= 1024,
  *    one channel of x is at most 16 MB, so the L2 window holds >= 2 channels): ONE persistent kernel working through an ordered queue of
  *    statistics and apply items, channel-major, with the apply items a ~32 MB window behind the
  *    statistics items, so the second read of x comes out of L2 -- HBM sees x once and y once;
@@ -147,7 +158,7 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig,
                  int stats_sweep, int apply_sweep,
                  void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
 
-/* Number of kernels maxstyle_fwd launches for this shape on the current device: 1 (fused), 3 (two-pass:
+/* Number of kernels maxstyle_fwd launches for this shape on the current device: 1 (resident or L2 window), 3 (two-pass:
  * stats, tables, apply), 0 for an unsupported shape.  Assumes 16-byte aligned x and y. */
 int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int stats_sweep);
 

@@ -3,10 +3,14 @@
 #include "kernels_nchw.cuh"
 #include "tables.cuh"
 #include "fused_fwd.cuh"
+#include "resident_fwd.cuh"
 #include "kernels_nhwc.cuh"
 
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 namespace {
 
@@ -221,9 +225,9 @@ void launch_fused(const FwdCall& f, const FusedArgs& a, int grid) {
 
 // Returns MAXSTYLE_OK after launching, -1 when this problem does not qualify (the caller then takes the
 // two-pass path), or an error code.
-int try_fused_fwd(const FwdCall& f, const Workspace& w, int sms) {
+int try_fused_fwd(const FwdCall& f, const Workspace& w, int sms, bool force) {
     const FusedPlan fp = make_fused_plan(f.N, f.C, f.M, f.dtype, common_align(f.x, f.y));
-    if (!fp.ok) return -1;
+    if (!fp.ok || (!fp.profitable && !force)) return -1;
     FusedArgs a;
     a.N = f.N; a.C = f.C; a.M = f.M;
     a.nvec = fp.nvec; a.pieces = fp.pieces; a.piece_vecs = fp.piece_vecs; a.items_per_channel = fp.items_per_channel;
@@ -247,6 +251,67 @@ int try_fused_fwd(const FwdCall& f, const Workspace& w, int sms) {
         if (fp.vec == 16) launch_fused<__nv_bfloat16, 16>(f, a, grid); else launch_fused<__nv_bfloat16, 8>(f, a, grid);
     }
     return check_launch();
+}
+
+// ---- resident forward ---------------------------------------------------------------------------------
+// CTAs of `kern` that fit one SM with `smem` bytes of dynamic shared memory (cached per device / kernel / size;
+// the first call also raises the kernel's dynamic shared memory limit).
+template <typename K>
+int resident_ctas_per_sm(K kern, int threads, int smem) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void*, int>, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    const auto key = std::make_tuple(dev, reinterpret_cast<const void*>(kern), smem);
+    std::lock_guard<std::mutex> lock(mu);
+    const auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    int k = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentMaxSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, kern, threads, (size_t)smem) != cudaSuccess) {
+        cudaGetLastError();
+        k = 0;
+    }
+    cache[key] = k;
+    return k;
+}
+
+template <typename T, int THREADS, int MINB>
+int launch_resident(const FwdCall& f, ResidentArgs& a, const ResidentPlan& rp, int sms) {
+    auto kern = fwd_resident_kernel<T, THREADS, MINB>;
+    const int k = resident_ctas_per_sm(kern, THREADS, rp.smem);
+    if (k <= 0) return -1;
+    const int64_t cap = (int64_t)sms * k;
+    const int grid = (int)(a.total_items < cap ? a.total_items : cap);
+    if (f.N > grid) return -1;                                 // the co-residency argument needs N <= grid
+    kern<<<grid, THREADS, rp.smem, f.stream>>>(static_cast<const T*>(f.x), static_cast<T*>(f.y), a);
+    return check_launch();
+}
+
+// Same contract as try_fused_fwd.
+int try_resident_fwd(const FwdCall& f, const Workspace& w, int sms, int stats_sweep, int apply_sweep, bool force) {
+    const ResidentPlan rp = make_resident_plan(f.N, f.C, f.M, f.dtype, common_align(f.x, f.y));
+    if (!rp.ok || (!rp.preferred && !force)) return -1;
+    ResidentArgs a;
+    a.N = f.N; a.C = f.C; a.M = f.M;
+    a.plane_bytes = rp.plane_bytes; a.chunk_bytes = rp.chunk_bytes; a.chunks = rp.chunks;
+    a.total_items = (int64_t)f.N * f.C;
+    a.flags = f.flags; a.eps = f.eps;
+    // x passes through L2 once; "keep" leaves the most recent part of it there for the backward sweep
+    a.in_policy = (stats_sweep & MAXSTYLE_SWEEP_X_KEEP) ? kPolicyKeep : kPolicyStream;
+    a.io_policy = (apply_sweep & MAXSTYLE_SWEEP_IO_NORMAL) ? kPolicyNormal : kPolicyStream;
+    a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
+    a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
+    a.gamma_std = f.gamma_std; a.beta_std = f.beta_std;
+    a.ready = reinterpret_cast<unsigned int*>(f.ws + w.plane_ready);
+    a.error = reinterpret_cast<int*>(f.ws + w.res_error);
+    a.queue = reinterpret_cast<unsigned long long*>(f.ws + w.res_error + 8);
+    a.done = reinterpret_cast<unsigned int*>(f.ws + w.res_error + 16);
+    if (f.dtype == MAXSTYLE_F32)
+        return rp.threads == 512 ? launch_resident<float, 512, 1>(f, a, rp, sms) : launch_resident<float, 256, 4>(f, a, rp, sms);
+    return rp.threads == 512 ? launch_resident<__nv_bfloat16, 512, 1>(f, a, rp, sms)
+                             : launch_resident<__nv_bfloat16, 256, 4>(f, a, rp, sms);
 }
 
 }  // namespace
@@ -353,7 +418,11 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
         if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
         FwdCall f{x, y, mu, sig, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, M, dtype, flags, eps,
                   static_cast<char*>(workspace), static_cast<cudaStream_t>(stream)};
-        rc = try_fused_fwd(f, w, sms);
+        if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RESIDENT)) {
+            rc = try_resident_fwd(f, w, sms, stats_sweep, apply_sweep, (stats_sweep & MAXSTYLE_SWEEP_FORCE_RESIDENT) != 0);
+            if (rc >= 0) return rc;
+        }
+        rc = try_fused_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW) != 0);
         if (rc >= 0) return rc;
     }
     rc = maxstyle_stats(x, mu, sig, C, 0, N, C, H, W, dtype, layout, eps, stats_sweep, workspace, workspace_bytes, stream);
@@ -367,7 +436,23 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
 int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int stats_sweep) {
     if (check_shape(N, C, H, W, dtype, layout) != MAXSTYLE_OK) return 0;
     if ((stats_sweep & MAXSTYLE_SWEEP_NO_FUSED) || is_nhwc(layout, C)) return 3;
-    return make_fused_plan(N, C, (int64_t)H * W, dtype, 32).ok ? 1 : 3;
+    const int64_t M = (int64_t)H * W;
+    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RESIDENT)) {
+        const ResidentPlan rp = make_resident_plan(N, C, M, dtype, 32);
+        if (rp.ok && (rp.preferred || (stats_sweep & MAXSTYLE_SWEEP_FORCE_RESIDENT))) {   // same grid rule as launch_resident
+            int k = 0;
+            if (dtype == MAXSTYLE_F32)
+                k = rp.threads == 512 ? resident_ctas_per_sm(fwd_resident_kernel<float, 512, 1>, 512, rp.smem)
+                                      : resident_ctas_per_sm(fwd_resident_kernel<float, 256, 4>, 256, rp.smem);
+            else
+                k = rp.threads == 512 ? resident_ctas_per_sm(fwd_resident_kernel<__nv_bfloat16, 512, 1>, 512, rp.smem)
+                                      : resident_ctas_per_sm(fwd_resident_kernel<__nv_bfloat16, 256, 4>, 256, rp.smem);
+            const int64_t cap = (int64_t)sm_count() * k, items = (int64_t)N * C;
+            if (k > 0 && N <= (items < cap ? items : cap)) return 1;
+        }
+    }
+    const FusedPlan fp = make_fused_plan(N, C, M, dtype, 32);
+    return fp.ok && (fp.profitable || (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW)) ? 1 : 3;
 }
 
 int maxstyle_workspace_status(const void* workspace, size_t workspace_bytes, int N, int C, int H, int W, int dtype, int layout,

@@ -152,7 +152,7 @@ __device__ __forceinline__ void fused_finalize_channel(const FusedArgs& a, int c
         float sc, sh;
         style_coeffs(fin_sig[n], fin_mu[n], fin_sig[pr], fin_mu[pr], mix, no_noise, mix ? a.lmda[n] : 0.f,
                      no_noise ? 0.f : a.gamma_noise[(int64_t)n * C + c], no_noise ? 0.f : a.beta_noise[(int64_t)n * C + c], gs, bs,
-                     sc, sh);
+                     sc, sh, !(a.flags & 8));
         a.scale[(int64_t)n * C + c] = sc;
         a.shift[(int64_t)n * C + c] = sh;
     }

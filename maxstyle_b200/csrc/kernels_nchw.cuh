@@ -28,10 +28,12 @@ struct TableRef {
 // Shared by tables_kernel and the fused forward so the two forward paths agree to the last bit.
 __device__ __forceinline__ void style_coeffs(float sg, float m, float sg_partner, float mu_partner, bool mix, bool no_noise,
                                              float lmda_raw, float gamma_noise, float beta_noise, float gs, float bs,
-                                             float& scale, float& shift) {
+                                             float& scale, float& shift, bool clamp = true) {
     float sg_mix = sg, mu_mix = m;
     if (mix) {
-        const float l = fminf(fmaxf(lmda_raw, 0.f), 1.f);
+        // MaxStyle clamps the mixing weight (maxstyle.py:173); MixStyle does not (mixstyle.py:95-96: a fixed lmda > 1
+        // or a Gaussian-sampled one extrapolates) -- MAXSTYLE_NO_CLAMP
+        const float l = clamp ? fminf(fmaxf(lmda_raw, 0.f), 1.f) : lmda_raw;
         sg_mix = sg * (1.f - l) + sg_partner * l;
         mu_mix = m * (1.f - l) + mu_partner * l;
     }
@@ -417,7 +419,7 @@ __device__ __forceinline__ void bwd_finalize_sample(int n, const BwdTables& tb, 
         float dl = 0.f;
         if (mix) {
             const float l = tb.lmda[n];
-            dl = (l >= 0.f && l <= 1.f) ? lam_acc : 0.f;      // clamp backward: closed interval
+            dl = ((tb.flags & 8) || (l >= 0.f && l <= 1.f)) ? lam_acc : 0.f;      // clamp backward: closed interval
         }
         if (tb.d_lmda) tb.d_lmda[n] = dl;
         if (st.mode != 0 && st.update_mix && mix)

@@ -121,15 +121,16 @@ stats_nhwc_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
         const int64_t n = pc.plane;
         const T* base = x + n * g.nvec * VEC;
         const int cvv = (int)((pc.v0 + (int64_t)t) % rg.cv);
-        float mean[VEC], m2[VEC], cnt = 0.f;
+        float mean[VEC], m2[VEC], K[VEC], cnt = 0.f;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) { mean[k] = 0.f; m2[k] = 0.f; }
+        for (int k = 0; k < VEC; ++k) { mean[k] = 0.f; m2[k] = 0.f; K[k] = 0.f; }
         if (t < A && pc.v0 + t < pc.v1) {
             int v = pc.v0 + t;
-            // The running mean doubles as the shift: deviations are taken from it BEFORE they are summed, so data
-            // whose spread is tiny against its mean loses no digits.  It starts at the thread's first value
-            // (count 0: the first merge has weight 1 and replaces it by that value + the batch's mean deviation).
-            Vec<T, VEC>::load(base + (int64_t)v * VEC, mean, pol);
+            // Fixed shift per (sample, channel): the sample's FIRST pixel.  Every value has K subtracted before
+            // anything is summed, so data whose spread is tiny against its mean loses no digits, and because all
+            // threads and all CTAs that share the sample use the same K, every merge (registers, shuffles, shared
+            // memory, per-CTA partials) happens between small shifted means; K is added back once, at the end.
+            Vec<T, VEC>::load(base + (int64_t)cvv * VEC, K, pol);
             for (; v + (VPT - 1) * A < pc.v1; v += VPT * A) {
                 float val[VPT][VEC];
 #pragma unroll
@@ -141,13 +142,14 @@ stats_nhwc_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
                 for (int k = 0; k < VEC; ++k) {
                     float s = 0.f;
 #pragma unroll
-                    for (int j = 0; j < VPT; ++j) { val[j][k] -= mean[k]; s += val[j][k]; }
-                    const float bm = s * (1.0f / (float)VPT);      // batch mean, relative to the running mean
+                    for (int j = 0; j < VPT; ++j) { val[j][k] -= K[k]; s += val[j][k]; }
+                    const float bm = s * (1.0f / (float)VPT);      // batch mean (shifted)
                     float q = 0.f;
 #pragma unroll
                     for (int j = 0; j < VPT; ++j) { const float d = val[j][k] - bm; q = fmaf(d, d, q); }
-                    mean[k] = fmaf(bm, w, mean[k]);
-                    m2[k] += fmaf(bm * bm, cw, q);
+                    const float dm = bm - mean[k];
+                    mean[k] = fmaf(dm, w, mean[k]);
+                    m2[k] += fmaf(dm * dm, cw, q);
                 }
                 cnt = nn;
             }
@@ -159,7 +161,7 @@ stats_nhwc_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
                 const float cw = cnt * w;
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
-                    const float dd = val[k] - mean[k];
+                    const float dd = (val[k] - K[k]) - mean[k];
                     mean[k] = fmaf(dd, w, mean[k]);
                     m2[k] = fmaf(dd * dd, cw, m2[k]);
                 }
@@ -172,7 +174,7 @@ stats_nhwc_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
             for (int c = t; c < C; c += kThreads) {
                 const Moments m = chan_moments<VEC>(c, nslots, rg, sh);
                 const int64_t o = ((int64_t)tr.row_offset + n) * tr.ld + c;
-                mu[o] = m.mean;
+                mu[o] = to_f32<T>(__ldg(base + c)) + m.mean;
                 sig[o] = sqrtf(m.m2 * inv_m1 + eps);
             }
         } else {
@@ -195,7 +197,7 @@ stats_nhwc_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
                         m = merge(m, Moments{v.x, v.y, v.z});
                     }
                     const int64_t o = ((int64_t)tr.row_offset + n) * tr.ld + c;
-                    mu[o] = m.mean;
+                    mu[o] = to_f32<T>(__ldg(base + c)) + m.mean;
                     sig[o] = sqrtf(m.m2 * inv_m1 + eps);
                 }
             }

@@ -116,6 +116,8 @@ constexpr int kFusedStreamThreads = kThreadsPerBlock - 32;   // 7 streaming warp
 constexpr int kFusedMaxN = 1024;                             // rows a finalising warp keeps in shared memory
 constexpr int64_t kFusedPieceBytes = 64 * 1024;              // target size of one item
 constexpr int64_t kFusedWindowBytes = 32ll << 20;            // x kept in L2 between statistics and apply
+constexpr int64_t kFusedProfitPlaneBytes = 64 * 1024;        // below this / above the next the two-pass path measured faster
+constexpr int64_t kFusedProfitChannelBytes = 8ll << 20;      // (profiles/r01_sweep.jsonl: 25 KB planes, 12.8 MB channels)
 constexpr int64_t kFusedMaxChannelBytes = 16ll << 20;        // the window must hold >= 2 channels: with one, every apply item
                                                              // waits for the finaliser of the channel streamed just before it
                                                              // (measured 2.3x slower than the two-pass path, profiles/r01_sweep.jsonl)
@@ -124,6 +126,7 @@ struct FusedPlan {
     bool ok;
     int vec, vpt, nvec, pieces, piece_vecs, items_per_channel, window, chunk;
     int64_t total_items;
+    bool profitable;   // expected to beat the two-pass path (maxstyle_fwd only takes it then, unless forced)
 };
 
 // vector loads a thread keeps in flight for one tensor (same rule as the streaming kernels)
@@ -163,18 +166,57 @@ inline FusedPlan make_fused_plan(int N, int C, int64_t M, int dtype, int align) 
     f.window = (int)d;
     f.total_items = 2ll * C * f.items_per_channel;
     f.chunk = (int)(chunk < 1 ? 1 : (chunk > 4 ? 4 : chunk));
+    f.profitable = M * es >= kFusedProfitPlaneBytes && channel_bytes <= kFusedProfitChannelBytes;
     f.ok = true;
     return f;
+}
+
+// ---- resident forward (resident_fwd.cuh): a plane stays in shared memory between statistics and apply ----
+constexpr int kResidentCtrlBytes = 4096;                     // == kResCtrlBytes
+constexpr int kResidentMaxChunks = 16;
+constexpr int kResidentMaxSmem = 232448;                     // 227 KB: the most one CTA may own on sm_100
+constexpr int kResidentMinPlaneBytes = 16 * 1024;            // smaller planes: the flag round trip per item dominates
+constexpr int kResidentMaxN = 304;                           // == kResMaxN
+
+struct ResidentPlan {
+    bool ok;
+    int threads;       // 512 (one CTA per SM: planes > ~108 KB) or 256
+    int plane_bytes, chunk_bytes, chunks;
+    int smem;          // dynamic shared memory per CTA
+    bool preferred;    // expected to beat the L2-window / two-pass paths (maxstyle_fwd only takes it then, unless forced)
+};
+
+inline ResidentPlan make_resident_plan(int N, int C, int64_t M, int dtype, int align) {
+    ResidentPlan r{};
+    const int64_t pb = M * elem_size(dtype);
+    if (align < 16 || pb % 16 != 0 || pb < kResidentMinPlaneBytes) return r;
+    if (N < 2 || N > kResidentMaxN) return r;
+    const int64_t smem = kResidentCtrlBytes + (pb + 127) / 128 * 128;
+    if (smem > kResidentMaxSmem) return r;
+    r.threads = 2 * (smem + 1024) > 228 * 1024 ? 512 : 256;  // does a second CTA fit on the SM?
+    const int consumers = r.threads - 32;
+    r.chunk_bytes = consumers * 16 * (r.threads >= 512 ? 2 : 4);
+    r.chunks = (int)ceil_div(pb, r.chunk_bytes);
+    if (r.chunks > kResidentMaxChunks) return r;
+    r.plane_bytes = (int)pb;
+    r.smem = (int)smem;
+    // Measured (profiles/r01_fwd_paths.txt): with >= 2 CTAs per SM the kernel beats the other paths by 10-15 % on tensors
+    // that do not fit L2; with one 196 KB plane per SM the load -> moments -> partner -> store chain of a plane is not
+    // hidden by anything else on the SM and the L2-window kernel wins; L2-sized tensors gain nothing from residency.
+    r.preferred = r.threads == 256 && (int64_t)N * C * pb >= (64ll << 20);
+    r.ok = true;
+    return r;
 }
 
 // Workspace layout (bytes):  [plane tickets: planes x u64][sample tickets: N x u64]
 //                            [done counter: 256 B][partials: planes x slots_bound x float4]
 //                            [fused forward: error flag + queue + done 256 B][arrived | ready: 2 x C x u32][item partials]
+//                            [resident forward: plane ready flags, planes x u32]
 // slots_bound covers every plan make_plan() can produce for this shape:
 //   slots = ceil(nvec/per) + 1  with  per >= total/kMaxGrid  =>  slots <= kMaxGrid/planes + 2.
 // NHWC (layout 1): the shared unit is the sample, each CTA publishes C partials for it (make_plan_nhwc).
 struct Workspace {
-    size_t plane_tickets, sample_tickets, done_counter, partials, res_error, res_flags, res_partials, total;
+    size_t plane_tickets, sample_tickets, done_counter, partials, res_error, res_flags, res_partials, plane_ready, total;
     int slots_bound;
 };
 
@@ -202,6 +244,7 @@ inline Workspace workspace_layout(int N, int C, int64_t M, int dtype, int layout
     w.res_error = off; off += 256;                           // int error @0, u64 queue @8, u32 done @16
     w.res_flags = off; off = align_up(off + (size_t)2 * C * sizeof(uint32_t), 256);
     w.res_partials = off; off = align_up(off + (size_t)items * 16, 256);
+    w.plane_ready = off; off = align_up(off + (size_t)planes * sizeof(uint32_t), 256);
     w.total = off;
     return w;
 }

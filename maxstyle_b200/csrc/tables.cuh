@@ -62,7 +62,7 @@ tables_kernel(const float* __restrict__ mu_all, const float* __restrict__ sig_al
         float sc, sh;
         style_coeffs(sg, m, sig_all[pr * ld + c], mu_all[pr * ld + c], mix, no_noise, mix ? lmda[n] : 0.f,
                      no_noise ? 0.f : gamma_noise[(int64_t)n * C + c], no_noise ? 0.f : beta_noise[(int64_t)n * C + c], gs, bs,
-                     sc, sh);
+                     sc, sh, !(flags & 8));
         scale[(int64_t)n * C + c] = sc;
         shift[(int64_t)n * C + c] = sh;
     }

@@ -422,8 +422,9 @@ FUSED_SHAPES = [
 
 @pytest.mark.parametrize("shape", FUSED_SHAPES)
 def test_fused_forward_matches_two_pass_and_oracle(shape):
-    """maxstyle_fwd's single-kernel fused path (ordered statistics/apply queue, x read from HBM once) against
-    the two-pass path and the float64 oracle; the workspace flags are left clean for the next call."""
+    """maxstyle_fwd's two single-kernel paths -- resident (plane held in shared memory between statistics and apply) and
+    L2 window (ordered statistics/apply queue) -- against the two-pass path and the float64 oracle, on the first-forward
+    variant (batch std computed in the kernel) and the cached-std variant; the workspace flags are left clean."""
     from maxstyle_b200 import functional as F, _lib as L
     n, c, h, w, dt = shape
     torch.manual_seed(n * 7 + c)
@@ -431,13 +432,16 @@ def test_fused_forward_matches_two_pass_and_oracle(shape):
     x_np = make_input(11 + n + c + h, (n, c, h, w))
     x = n2t(x_np, dt)
     code = F.dtype_code(x)
-    assert L.get_lib().maxstyle_fwd_kernels(n, c, h, w, code, L.NCHW, 0) == 1, "shape should qualify for the fused path"
+    lib = L.get_lib()
+    assert lib.maxstyle_fwd_kernels(n, c, h, w, code, L.NCHW, L.SWEEP_FORCE_RESIDENT) == 1, "shape should qualify for the resident path"
+    window = L.SWEEP_NO_RESIDENT | L.SWEEP_FORCE_WINDOW
+    assert lib.maxstyle_fwd_kernels(n, c, h, w, code, L.NCHW, window) == 1, "shape should qualify for the L2-window path"
+    assert lib.maxstyle_fwd_kernels(n, c, h, w, code, L.NCHW, L.SWEEP_NO_FUSED) == 3
     ws = F.new_workspace(n, c, h, w, code, x.device)
     perm = layer.perm.to(x.device)
-    flags = L.FLAG_MIX_STYLE | L.FLAG_COMPUTE_BATCH_STD
     outs = {}
-    for name, sweep in (("fused", 0), ("two_pass", L.SWEEP_NO_FUSED), ("fused_again", 0)):
-        gs = torch.zeros(c, device=x.device); bs = torch.zeros(c, device=x.device)
+
+    def run(name, sweep, gs, bs, flags):
         old = F.SWEEP_STATS
         F.SWEEP_STATS = sweep
         try:
@@ -447,17 +451,58 @@ def test_fused_forward_matches_two_pass_and_oracle(shape):
             F.SWEEP_STATS = old
         F.workspace_status(ws, n, c, h, w, code)
         outs[name] = [t.clone() for t in (y, mu, sig, scale, shift, gs, bs)]
+
+    first = L.FLAG_MIX_STYLE | L.FLAG_COMPUTE_BATCH_STD
+    res = L.SWEEP_FORCE_RESIDENT
+    for name, sweep in (("resident", res), ("window", window), ("two_pass", L.SWEEP_NO_FUSED), ("resident_again", res), ("default", 0)):
+        run(name, sweep, torch.zeros(c, device=x.device), torch.zeros(c, device=x.device), first)
+    # later forwards of the same module: gamma_std / beta_std are inputs, a plane only waits for its partner
+    gs0, bs0 = outs["two_pass"][5], outs["two_pass"][6]
+    run("resident_cached", res, gs0.clone(), bs0.clone(), L.FLAG_MIX_STYLE)
+    run("two_pass_cached", L.SWEEP_NO_FUSED, gs0.clone(), bs0.clone(), L.FLAG_MIX_STYLE)
     tol = 2.0 ** -8 if dt == torch.bfloat16 else 2e-6
-    for i, nm in enumerate(("y", "mu", "sig", "scale", "shift", "gamma_std", "beta_std")):
-        a, b = t2n(outs["fused"][i]), t2n(outs["two_pass"][i])
-        assert_rel(a, b, tol if nm == "y" else 1e-5, f"{nm}: fused vs two-pass", scale=max(np.abs(b).max(), 1e-3))
-        assert torch.equal(outs["fused"][i], outs["fused_again"][i]), f"{nm}: fused path not deterministic"
+    names = ("y", "mu", "sig", "scale", "shift", "gamma_std", "beta_std")
+    for cand, ref in (("resident", "two_pass"), ("window", "two_pass"), ("default", "two_pass"), ("resident_cached", "two_pass_cached")):
+        for i, nm in enumerate(names):
+            a, b = t2n(outs[cand][i]), t2n(outs[ref][i])
+            assert_rel(a, b, tol if nm == "y" else 1e-5, f"{nm}: {cand} vs {ref}", scale=max(np.abs(b).max(), 1e-3))
+    for i, nm in enumerate(names):
+        assert torch.equal(outs["resident"][i], outs["resident_again"][i]), f"{nm}: resident path not deterministic"
     st = oracle_state(layer.perm.numpy(), t2n(layer.gamma_noise).reshape(n, c), t2n(layer.beta_noise).reshape(n, c),
                       t2n(layer.lmda).reshape(n), {})
     y64, cache = O.forward(t2n(x), st, dtype=np.float64)
-    assert_rel(t2n(outs["fused"][0]), y64, tol if dt == torch.bfloat16 else FWD_RTOL, "y fused vs f64 oracle")
-    assert_rel(t2n(outs["fused"][1]), cache.mu, 1e-6, "mu", scale=max(np.abs(cache.mu).max(), 1e-3))
-    assert np.abs(t2n(outs["fused"][2]) / cache.sig - 1).max() < 1e-5
+    for cand in ("resident", "window", "resident_cached"):
+        assert_rel(t2n(outs[cand][0]), y64, tol if dt == torch.bfloat16 else FWD_RTOL, f"y {cand} vs f64 oracle")
+        assert_rel(t2n(outs[cand][1]), cache.mu, 1e-6, "mu", scale=max(np.abs(cache.mu).max(), 1e-3))
+        assert np.abs(t2n(outs[cand][2]) / cache.sig - 1).max() < 1e-5
+
+
+def test_resident_forward_flag_variants_and_fixed_points():
+    """Resident kernel on the flag variants (no mixing, no noise) and with a permutation that has fixed points
+    (a plane that is its own partner must not wait), against the two-pass path bit for bit on the tables' inputs."""
+    from maxstyle_b200 import functional as F, _lib as L
+    n, c, h, w = 6, 4, 80, 80
+    x = n2t(make_input(5, (n, c, h, w)))
+    ws = F.new_workspace(n, c, h, w, L.F32, x.device)
+    g = torch.Generator().manual_seed(3)
+    gamma, beta = torch.randn(n, c, generator=g).cuda(), torch.randn(n, c, generator=g).cuda()
+    lmda = torch.rand(n, generator=g).cuda()
+    perm = torch.tensor([0, 2, 1, 3, 5, 4], dtype=torch.int64).cuda()      # fixed points 0 and 3
+    for flags in (L.FLAG_MIX_STYLE | L.FLAG_COMPUTE_BATCH_STD, L.FLAG_MIX_STYLE | L.FLAG_NO_NOISE, L.FLAG_COMPUTE_BATCH_STD):
+        res = {}
+        for name, sweep in (("resident", L.SWEEP_FORCE_RESIDENT), ("two_pass", L.SWEEP_NO_FUSED)):
+            gs, bs = torch.zeros(c, device=x.device), torch.zeros(c, device=x.device)
+            old = F.SWEEP_STATS
+            F.SWEEP_STATS = sweep
+            try:
+                out = F.forward_raw(x, perm, lmda, gamma, beta, gs, bs, flags, 1e-6, ws)
+            finally:
+                F.SWEEP_STATS = old
+            F.workspace_status(ws, n, c, h, w, L.F32)
+            res[name] = [t.clone() for t in out] + [gs, bs]
+        for i, nm in enumerate(("y", "mu", "sig", "scale", "shift", "gamma_std", "beta_std")):
+            a, b = t2n(res["resident"][i]), t2n(res["two_pass"][i])
+            assert_rel(a, b, 2e-6 if nm == "y" else 1e-5, f"flags {flags} {nm}", scale=max(np.abs(b).max(), 1e-3))
 
 
 def test_fused_forward_declines_what_it_cannot_hold():
@@ -467,3 +512,5 @@ def test_fused_forward_declines_what_it_cannot_hold():
     assert lib.maxstyle_fwd_kernels(6, 2, 37, 41, 0, 0, 0) == 3           # planes not a multiple of 16 bytes
     assert lib.maxstyle_fwd_kernels(64, 8, 28, 28, 0, 0, 0) == 3          # 3 KB planes: warp-per-plane kernels
     assert lib.maxstyle_fwd_kernels(20, 64, 224, 224, 0, 0, L.SWEEP_NO_FUSED) == 3
+    assert lib.maxstyle_fwd_kernels(512, 64, 112, 112, 1, 0, 0) == 3      # N > co-resident CTAs and a 12.8 MB channel: two-pass
+    assert lib.maxstyle_fwd_kernels(512, 64, 112, 112, 1, 0, L.SWEEP_FORCE_WINDOW) == 1
