@@ -80,7 +80,9 @@ enum {
     MAXSTYLE_SWEEP_NO_RESIDENT = 32, /* maxstyle_fwd (stats_sweep): skip the shared-memory-resident kernel */
     MAXSTYLE_SWEEP_FORCE_WINDOW = 64, /* maxstyle_fwd (stats_sweep): take the L2-window kernel whenever the
                                         shape qualifies, even where the two-pass path is faster (tests)   */
-    MAXSTYLE_SWEEP_FORCE_RESIDENT = 128 /* ... likewise for the shared-memory-resident kernel               */
+    MAXSTYLE_SWEEP_FORCE_RESIDENT = 128, /* ... likewise for the shared-memory-resident kernel              */
+    MAXSTYLE_SWEEP_NO_RING = 256,   /* maxstyle_fwd (stats_sweep): skip the TMA-ring version of the L2-window kernel */
+    MAXSTYLE_SWEEP_FORCE_RING = 512 /* ... take it whenever the shape qualifies                              */
 };
 
 /* optimiser step fused into the backward epilogue (north_star item 4) */
@@ -146,6 +148,9 @@ int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, in
  *    kernel; each plane is brought into shared memory once by TMA bulk copies, its moments are taken there, the
  *    CTA exchanges (mu, sig) with its mixing partner's CTA through global flags, and y is written from shared
  *    memory while the next plane is already loading -- HBM sees x once and y once, L2 is only passed through;
+ *  - L2 window, streamed (same rule as the next one): the ordered statistics/apply queue described below, but x moves
+ *    through a ring of TMA bulk copies that one producer thread keeps full across item boundaries, and the
+ *    consumer warps work out of shared memory;
  *  - L2 window (when the shape qualifies and it pays: planes >= 64 KB, a channel <= 8 MB: planes are 16-byte multiples of at least 8-16 KB, 2 <= N <= 1024,
  *    one channel of x is at most 16 MB, so the L2 window holds >= 2 channels): ONE persistent kernel working through an ordered queue of
  *    statistics and apply items, channel-major, with the apply items a ~32 MB window behind the

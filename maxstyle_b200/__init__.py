@@ -2,9 +2,10 @@
 cherise215/MaxStyle `src/advanced/maxstyle.py`) over hand-written sm_100a CUDA kernels."""
 from .layer import MaxStyle
 from .optim import FusedStyleOptimizer
+from .mixstyle import MixStyle
 from .distributed import GlobalBatchMaxStyle, StyleTableExchange
 from .host_pipeline import HostStepPipeline, HostStepResult
 
-__all__ = ["MaxStyle", "FusedStyleOptimizer", "GlobalBatchMaxStyle", "StyleTableExchange",
+__all__ = ["MaxStyle", "MixStyle", "FusedStyleOptimizer", "GlobalBatchMaxStyle", "StyleTableExchange",
            "HostStepPipeline", "HostStepResult"]
 __version__ = "0.1.0"

@@ -19,7 +19,7 @@ NCHW, NHWC = 0, 1
 FLAG_MIX_STYLE, FLAG_NO_NOISE, FLAG_COMPUTE_BATCH_STD, FLAG_NO_CLAMP = 1, 2, 4, 8
 STEP_NONE, STEP_ADAM, STEP_SIGN = 0, 1, 2
 SWEEP_REVERSE, SWEEP_X_KEEP, SWEEP_X_STREAM, SWEEP_IO_NORMAL, SWEEP_NO_FUSED = 1, 2, 4, 8, 16
-SWEEP_NO_RESIDENT, SWEEP_FORCE_WINDOW, SWEEP_FORCE_RESIDENT = 32, 64, 128
+SWEEP_NO_RESIDENT, SWEEP_FORCE_WINDOW, SWEEP_FORCE_RESIDENT, SWEEP_NO_RING, SWEEP_FORCE_RING = 32, 64, 128, 256, 512
 
 _f32p = C.c_void_p      # device pointers travel as plain addresses
 _vp = C.c_void_p

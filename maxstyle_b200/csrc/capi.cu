@@ -4,6 +4,7 @@
 #include "tables.cuh"
 #include "fused_fwd.cuh"
 #include "resident_fwd.cuh"
+#include "ring_fwd.cuh"
 #include "kernels_nhwc.cuh"
 
 #include <cuda_runtime.h>
@@ -253,6 +254,58 @@ int try_fused_fwd(const FwdCall& f, const Workspace& w, int sms, bool force) {
     return check_launch();
 }
 
+// ---- streamed forward (TMA ring) ------------------------------------------------------------------------
+template <typename T>
+int launch_ring(const FwdCall& f, const FusedArgs& a, const RingPlan& rp, int sms) {
+    auto kern = fwd_ring_kernel<T>;
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, int> cache;          // (device, smem) -> CTAs per SM
+    int dev = 0, k = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        const auto key = std::make_pair(dev, rp.smem);
+        const auto it = cache.find(key);
+        if (it != cache.end()) k = it->second;
+        else {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingCtrl + kRingMaxStages * kRingChunk) != cudaSuccess ||
+                cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, kern, kThreads, (size_t)rp.smem) != cudaSuccess) {
+                cudaGetLastError();
+                k = 0;
+            }
+            cache[key] = k;
+        }
+    }
+    if (k <= 0) return -1;
+    const int64_t cap = (int64_t)sms * k;
+    const int grid = (int)(rp.total_items < cap ? rp.total_items : cap);
+    RingGeom rg{rp.stages, rp.plane_bytes, rp.piece_bytes};
+    kern<<<grid, kThreads, rp.smem, f.stream>>>(static_cast<const T*>(f.x), static_cast<T*>(f.y), a, rg);
+    return check_launch();
+}
+
+// Same contract as try_fused_fwd.
+int try_ring_fwd(const FwdCall& f, const Workspace& w, int sms, bool force) {
+    const RingPlan rp = make_ring_plan(f.N, f.C, f.M, f.dtype, common_align(f.x, f.y));
+    if (!rp.ok || (!rp.profitable && !force)) return -1;
+    FusedArgs a{};
+    a.N = f.N; a.C = f.C; a.M = f.M;
+    a.pieces = rp.pieces; a.items_per_channel = rp.items_per_channel;
+    a.window = rp.window; a.chunk = 1; a.total_items = rp.total_items;
+    a.flags = f.flags; a.eps = f.eps;
+    a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
+    a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
+    a.gamma_std = f.gamma_std; a.beta_std = f.beta_std;
+    a.partials = reinterpret_cast<float4*>(f.ws + w.res_partials);
+    unsigned int* fl = reinterpret_cast<unsigned int*>(f.ws + w.res_flags);
+    a.arrived = fl; a.ready = fl + f.C;
+    a.error = reinterpret_cast<int*>(f.ws + w.res_error);
+    a.queue = reinterpret_cast<unsigned long long*>(f.ws + w.res_error + 8);
+    a.done = reinterpret_cast<unsigned int*>(f.ws + w.res_error + 16);
+    return f.dtype == MAXSTYLE_F32 ? launch_ring<float>(f, a, rp, sms) : launch_ring<__nv_bfloat16>(f, a, rp, sms);
+}
+
 // ---- resident forward ---------------------------------------------------------------------------------
 // CTAs of `kern` that fit one SM with `smem` bytes of dynamic shared memory (cached per device / kernel / size;
 // the first call also raises the kernel's dynamic shared memory limit).
@@ -422,6 +475,10 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
             rc = try_resident_fwd(f, w, sms, stats_sweep, apply_sweep, (stats_sweep & MAXSTYLE_SWEEP_FORCE_RESIDENT) != 0);
             if (rc >= 0) return rc;
         }
+        if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RING)) {
+            rc = try_ring_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_RING) != 0);
+            if (rc >= 0) return rc;
+        }
         rc = try_fused_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW) != 0);
         if (rc >= 0) return rc;
     }
@@ -450,6 +507,10 @@ int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int 
             const int64_t cap = (int64_t)sm_count() * k, items = (int64_t)N * C;
             if (k > 0 && N <= (items < cap ? items : cap)) return 1;
         }
+    }
+    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RING)) {
+        const RingPlan gp = make_ring_plan(N, C, M, dtype, 32);
+        if (gp.ok && (gp.profitable || (stats_sweep & MAXSTYLE_SWEEP_FORCE_RING))) return 1;
     }
     const FusedPlan fp = make_fused_plan(N, C, M, dtype, 32);
     return fp.ok && (fp.profitable || (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW)) ? 1 : 3;

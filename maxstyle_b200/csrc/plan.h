@@ -171,6 +171,42 @@ inline FusedPlan make_fused_plan(int N, int C, int64_t M, int dtype, int align) 
     return f;
 }
 
+// ---- streamed forward (ring_fwd.cuh): the window queue fed through a TMA ring -------------------------------
+constexpr int kRingChunk = kFusedStreamThreads * 16 * 4;     // == kRingChunkBytes (14336)
+constexpr int kRingCtrl = 12288;                             // == kRingCtrlBytes
+
+struct RingPlan {
+    bool ok;
+    int stages, plane_bytes, piece_bytes, pieces, items_per_channel, window, smem;
+    int64_t total_items;
+    bool profitable;
+};
+
+inline RingPlan make_ring_plan(int N, int C, int64_t M, int dtype, int align) {
+    static const int64_t piece_chunks = env_or("MAXSTYLE_RING_PIECE_CHUNKS", 4, 1);
+    static const int64_t stages = env_or("MAXSTYLE_RING_STAGES", 4, 1);
+    static const int64_t window_bytes = env_or("MAXSTYLE_FUSED_WINDOW_MB", kFusedWindowBytes, 1 << 20);
+    RingPlan r{};
+    const int64_t pb = M * elem_size(dtype);
+    const int64_t channel_bytes = (int64_t)N * pb;
+    if (align < 16 || pb % 16 != 0 || pb < 8192 || pb > 0x7fffffff) return r;
+    if (N < 2 || N > kFusedMaxN || channel_bytes > kFusedMaxChannelBytes) return r;
+    r.stages = (int)(stages < 2 ? 2 : (stages > 8 ? 8 : stages));
+    r.plane_bytes = (int)pb;
+    r.piece_bytes = (int)(piece_chunks < 1 ? 1 : piece_chunks) * kRingChunk;
+    r.pieces = (int)ceil_div(pb, r.piece_bytes);
+    r.items_per_channel = N * r.pieces;
+    int64_t d = window_bytes / channel_bytes;
+    if (d < 1) d = 1;
+    if (d > C) d = C;
+    r.window = (int)d;
+    r.total_items = 2ll * C * r.items_per_channel;
+    r.smem = kRingCtrl + r.stages * kRingChunk;
+    r.profitable = pb >= kFusedProfitPlaneBytes && channel_bytes <= kFusedProfitChannelBytes;
+    r.ok = true;
+    return r;
+}
+
 // ---- resident forward (resident_fwd.cuh): a plane stays in shared memory between statistics and apply ----
 constexpr int kResidentCtrlBytes = 4096;                     // == kResCtrlBytes
 constexpr int kResidentMaxChunks = 16;
@@ -240,6 +276,10 @@ inline Workspace workspace_layout(int N, int C, int64_t M, int dtype, int layout
     for (int align = 16; align <= 32; align *= 2) {
         const FusedPlan fp = make_fused_plan(N, C, M, dtype, align);
         if (fp.ok && (int64_t)C * fp.items_per_channel > items) items = (int64_t)C * fp.items_per_channel;
+    }
+    {
+        const RingPlan rp = make_ring_plan(N, C, M, dtype, 16);
+        if (rp.ok && (int64_t)C * rp.items_per_channel > items) items = (int64_t)C * rp.items_per_channel;
     }
     w.res_error = off; off += 256;                           // int error @0, u64 queue @8, u32 done @16
     w.res_flags = off; off = align_up(off + (size_t)2 * C * sizeof(uint32_t), 256);

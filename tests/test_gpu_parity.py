@@ -434,7 +434,9 @@ def test_fused_forward_matches_two_pass_and_oracle(shape):
     code = F.dtype_code(x)
     lib = L.get_lib()
     assert lib.maxstyle_fwd_kernels(n, c, h, w, code, L.NCHW, L.SWEEP_FORCE_RESIDENT) == 1, "shape should qualify for the resident path"
-    window = L.SWEEP_NO_RESIDENT | L.SWEEP_FORCE_WINDOW
+    window = L.SWEEP_NO_RESIDENT | L.SWEEP_NO_RING | L.SWEEP_FORCE_WINDOW
+    ring = L.SWEEP_NO_RESIDENT | L.SWEEP_FORCE_RING
+    assert lib.maxstyle_fwd_kernels(n, c, h, w, code, L.NCHW, ring) == 1, "shape should qualify for the streamed (TMA ring) path"
     assert lib.maxstyle_fwd_kernels(n, c, h, w, code, L.NCHW, window) == 1, "shape should qualify for the L2-window path"
     assert lib.maxstyle_fwd_kernels(n, c, h, w, code, L.NCHW, L.SWEEP_NO_FUSED) == 3
     ws = F.new_workspace(n, c, h, w, code, x.device)
@@ -454,7 +456,8 @@ def test_fused_forward_matches_two_pass_and_oracle(shape):
 
     first = L.FLAG_MIX_STYLE | L.FLAG_COMPUTE_BATCH_STD
     res = L.SWEEP_FORCE_RESIDENT
-    for name, sweep in (("resident", res), ("window", window), ("two_pass", L.SWEEP_NO_FUSED), ("resident_again", res), ("default", 0)):
+    for name, sweep in (("resident", res), ("window", window), ("ring", ring), ("two_pass", L.SWEEP_NO_FUSED),
+                        ("resident_again", res), ("ring_again", ring), ("default", 0)):
         run(name, sweep, torch.zeros(c, device=x.device), torch.zeros(c, device=x.device), first)
     # later forwards of the same module: gamma_std / beta_std are inputs, a plane only waits for its partner
     gs0, bs0 = outs["two_pass"][5], outs["two_pass"][6]
@@ -462,16 +465,19 @@ def test_fused_forward_matches_two_pass_and_oracle(shape):
     run("two_pass_cached", L.SWEEP_NO_FUSED, gs0.clone(), bs0.clone(), L.FLAG_MIX_STYLE)
     tol = 2.0 ** -8 if dt == torch.bfloat16 else 2e-6
     names = ("y", "mu", "sig", "scale", "shift", "gamma_std", "beta_std")
-    for cand, ref in (("resident", "two_pass"), ("window", "two_pass"), ("default", "two_pass"), ("resident_cached", "two_pass_cached")):
+    run("ring_cached", ring, gs0.clone(), bs0.clone(), L.FLAG_MIX_STYLE)
+    for cand, ref in (("resident", "two_pass"), ("window", "two_pass"), ("ring", "two_pass"), ("default", "two_pass"),
+                      ("resident_cached", "two_pass_cached"), ("ring_cached", "two_pass_cached")):
         for i, nm in enumerate(names):
             a, b = t2n(outs[cand][i]), t2n(outs[ref][i])
             assert_rel(a, b, tol if nm == "y" else 1e-5, f"{nm}: {cand} vs {ref}", scale=max(np.abs(b).max(), 1e-3))
     for i, nm in enumerate(names):
         assert torch.equal(outs["resident"][i], outs["resident_again"][i]), f"{nm}: resident path not deterministic"
+        assert torch.equal(outs["ring"][i], outs["ring_again"][i]), f"{nm}: streamed path not deterministic"
     st = oracle_state(layer.perm.numpy(), t2n(layer.gamma_noise).reshape(n, c), t2n(layer.beta_noise).reshape(n, c),
                       t2n(layer.lmda).reshape(n), {})
     y64, cache = O.forward(t2n(x), st, dtype=np.float64)
-    for cand in ("resident", "window", "resident_cached"):
+    for cand in ("resident", "window", "ring", "resident_cached", "ring_cached"):
         assert_rel(t2n(outs[cand][0]), y64, tol if dt == torch.bfloat16 else FWD_RTOL, f"y {cand} vs f64 oracle")
         assert_rel(t2n(outs[cand][1]), cache.mu, 1e-6, "mu", scale=max(np.abs(cache.mu).max(), 1e-3))
         assert np.abs(t2n(outs[cand][2]) / cache.sig - 1).max() < 1e-5
@@ -513,4 +519,4 @@ def test_fused_forward_declines_what_it_cannot_hold():
     assert lib.maxstyle_fwd_kernels(64, 8, 28, 28, 0, 0, 0) == 3          # 3 KB planes: warp-per-plane kernels
     assert lib.maxstyle_fwd_kernels(20, 64, 224, 224, 0, 0, L.SWEEP_NO_FUSED) == 3
     assert lib.maxstyle_fwd_kernels(512, 64, 112, 112, 1, 0, 0) == 3      # N > co-resident CTAs and a 12.8 MB channel: two-pass
-    assert lib.maxstyle_fwd_kernels(512, 64, 112, 112, 1, 0, L.SWEEP_FORCE_WINDOW) == 1
+    assert lib.maxstyle_fwd_kernels(512, 64, 112, 112, 1, 0, L.SWEEP_NO_RING | L.SWEEP_FORCE_WINDOW) == 1

@@ -64,17 +64,33 @@ def to_bytes(val, unit):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
 
+REPORTS = {   # capture -> the command it was taken from (tools/gpu_profile.sh)
+    "prof.ncu-rep": "python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline",
+    "prof2.ncu-rep": "MAXSTYLE_SWEEP=18,3,4 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline   (two-pass forward forced)",
+    "prof3.ncu-rep": "python tools/kernel_bench.py --fwd-only --dtype bf16 --sweeps 2,3,4 --iters 10   (bf16 config-1 shape)",
+    "prof4.ncu-rep": "python tools/kernel_bench.py --layout nhwc --sweeps 2,2,4   (NHWC kernels)",
+}
+
+
 def ncu(src, out, traffic_path):
-    rep = os.path.join(src, "prof.ncu-rep")
+    traffic = {}
+    with open(out, "w") as f:
+        f.write("ncu --set full --clock-control none --import-source on  (one launch per kernel; cold caches)\n")
+        for rep_name, cmd in REPORTS.items():
+            rep = os.path.join(src, rep_name)
+            if os.path.exists(rep):
+                ncu_one(rep, cmd, f, traffic)
+    json.dump(traffic, open(traffic_path, "w"), indent=1)
+
+
+def ncu_one(rep, cmd, f, traffic):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     stall = [h for h in hdr if h.startswith("smsp__pcsamp_warps_issue_stalled") and not h.endswith("not_issued")]
-    traffic = {}
-    with open(out, "w") as f:
-        f.write("ncu --set full --clock-control none --import-source on  (one launch per kernel; cold caches)\n")
-        f.write(f"command: python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline   (source: {rep})\n")
+    if True:
+        f.write(f"\ncommand: {cmd}   (source: {rep})\n")
         for r in rows[2:]:
             name = short(r[idx["Kernel Name"]])
             f.write(f"\n== {name}\n")
@@ -87,9 +103,10 @@ def ncu(src, out, traffic_path):
             rd = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
             wr = to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
             key = name.split("<")[0]
+            if key in traffic:
+                key = name
             traffic[key] = {"dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr, "kernel": name,
                             "duration_us_under_ncu": float(r[idx["gpu__time_duration.sum"]].replace(",", ""))}
-    json.dump(traffic, open(traffic_path, "w"), indent=1)
 
 
 def main():
@@ -97,7 +114,8 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     launches(src, os.path.join(ROOT, "profiles", f"{name}_launches.txt"))
     ncu(src, os.path.join(ROOT, "profiles", f"{name}_ncu.txt"), os.path.join(ROOT, "profiles", "traffic.json"))
-    for extra in ("bench.json", "bench_ref.json", "pytest_gpu.txt", "smoke.txt"):
+    for extra in ("bench.json", "bench_ref.json", "pytest_gpu.txt", "smoke.txt", "fwd_paths.txt", "configs.jsonl", "sweep.jsonl",
+                  "loop_config2.txt", "ring_knobs.txt"):
         p = os.path.join(src, extra)
         if os.path.exists(p):
             with open(p) as fi, open(os.path.join(ROOT, "profiles", f"{name}_{extra}"), "w") as fo:

@@ -84,6 +84,8 @@ def main():
     ap.add_argument("--max-gb", type=float, default=8.0, help="skip points whose tensors exceed this many GB each")
     ap.add_argument("--iters", type=int, default=9)
     ap.add_argument("--out", default="")
+    ap.add_argument("--points", default="", help='explicit points instead of the grid: "N,C,H,W,dtype,layout;..." '
+                    '(e.g. BASELINE config 5 per GPU: 256,32,512,512,f32,NCHW)')
     args = ap.parse_args()
     peak, src = hbm_peak()
     Ns, Cs, Ss = [64, 128, 256, 512], [16, 32, 64, 128, 256], [28, 56, 112, 224]
@@ -95,6 +97,16 @@ def main():
             "note": "step = maxstyle_fwd + maxstyle_bwd with fused Adam through the C ABI; 5*E*s algorithmic bytes"}
     print(json.dumps(head)); out and out.write(json.dumps(head) + "\n")
     skipped = 0
+    if args.points:
+        for spec in args.points.split(";"):
+            n, c, h, w, dtype, layout = spec.split(",")
+            r = point(int(n), int(c), int(h), int(w), dtype, layout, args.iters, flush, peak)
+            line = json.dumps(r)
+            print(line, flush=True)
+            if out:
+                out.write(line + "\n"); out.flush()
+            torch.cuda.empty_cache()
+        return
     for dtype in ("f32", "bf16"):
         for layout in ("NCHW", "NHWC"):
             for n in Ns:
