@@ -5,7 +5,8 @@ from .optim import FusedStyleOptimizer
 from .mixstyle import MixStyle
 from .distributed import GlobalBatchMaxStyle, StyleTableExchange
 from .host_pipeline import HostStepPipeline, HostStepResult
+from .executor import StyleLoopExecutor
 
 __all__ = ["MaxStyle", "MixStyle", "FusedStyleOptimizer", "GlobalBatchMaxStyle", "StyleTableExchange",
-           "HostStepPipeline", "HostStepResult"]
+           "HostStepPipeline", "HostStepResult", "StyleLoopExecutor"]
 __version__ = "0.1.0"

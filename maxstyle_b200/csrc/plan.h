@@ -183,7 +183,7 @@ struct RingPlan {
 };
 
 inline RingPlan make_ring_plan(int N, int C, int64_t M, int dtype, int align) {
-    static const int64_t piece_chunks = env_or("MAXSTYLE_RING_PIECE_CHUNKS", 4, 1);
+    static const int64_t piece_chunks = env_or("MAXSTYLE_RING_PIECE_CHUNKS", 8, 1);
     static const int64_t stages = env_or("MAXSTYLE_RING_STAGES", 4, 1);
     static const int64_t window_bytes = env_or("MAXSTYLE_FUSED_WINDOW_MB", kFusedWindowBytes, 1 << 20);
     RingPlan r{};
@@ -202,7 +202,11 @@ inline RingPlan make_ring_plan(int N, int C, int64_t M, int dtype, int align) {
     r.window = (int)d;
     r.total_items = 2ll * C * r.items_per_channel;
     r.smem = kRingCtrl + r.stages * kRingChunk;
-    r.profitable = pb >= kFusedProfitPlaneBytes && channel_bytes <= kFusedProfitChannelBytes;
+    // Measured equal to the register-staged window kernel within 2 % (profiles/r01_ring_knobs.txt: 110.7 vs 113.3 us on
+    // the config-1 shape with 8-chunk pieces): the window kernel stays the default, MAXSTYLE_RING=1 or
+    // MAXSTYLE_SWEEP_FORCE_RING select this one.
+    static const int64_t prefer = env_or("MAXSTYLE_RING", 0, 1);
+    r.profitable = prefer > 0 && pb >= kFusedProfitPlaneBytes && channel_bytes <= kFusedProfitChannelBytes;
     r.ok = true;
     return r;
 }

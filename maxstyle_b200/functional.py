@@ -268,6 +268,9 @@ class MaxStyleFunction(torch.autograd.Function):
             gamma_std = torch.empty(1, layer.num_feature, 1, 1, dtype=torch.float32, device=x.device)
             beta_std = torch.empty(1, layer.num_feature, 1, 1, dtype=torch.float32, device=x.device)
             flags |= L.FLAG_COMPUTE_BATCH_STD
+        elif getattr(layer, "_redraw_batch_std", False):       # reinit_(): recompute into the existing buffers
+            gamma_std, beta_std = layer.gamma_std, layer.beta_std
+            flags |= L.FLAG_COMPUTE_BATCH_STD
         else:
             gamma_std, beta_std = layer.gamma_std, layer.beta_std
         ws = layer._workspace_for(x)
@@ -275,6 +278,7 @@ class MaxStyleFunction(torch.autograd.Function):
                                                gamma_std, beta_std, flags, layer.eps, ws)
         if first:                      # cached until reset(), like the reference (maxstyle.py:165-168)
             layer.gamma_std, layer.beta_std = gamma_std, beta_std
+        layer._redraw_batch_std = False
         ctx.layer = layer
         ctx.flags = flags & ~L.FLAG_COMPUTE_BATCH_STD
         ctx.tables = (mu, sig, scale, gamma_std, beta_std)

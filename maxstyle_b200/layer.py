@@ -147,6 +147,38 @@ class MaxStyle(nn.Module):
             self.__dict__.pop(name, None)
         super().__setattr__(name, value)
 
+    @torch.no_grad()
+    def reinit_(self, storage_active: bool = True):
+        """In-place `reset()` for CUDA-graph replay (StyleLoopExecutor): re-draws perm / rand_p / parameters with exactly the
+        generator consumption of `init_parameters()` (so a seeded run matches three fresh constructions in the reference's
+        loop, model:522-527) but writes into the EXISTING tensors -- parameter, permutation, batch-std and optimiser-state
+        addresses captured in a graph stay valid.  Requires a module built with every learnable it can ever need
+        (construct with p=1.0 storage via StyleLoopExecutor); returns whether the layer is active for this draw."""
+        n, c, dev = self.batch_size, self.num_feature, self.device
+        self.perm = self._draw_permutation()
+        if self._perm_dev is not None:
+            self._perm_dev.copy_(self.perm.to(torch.int64), non_blocking=False)
+        self.rand_p = torch.rand(1)
+        active = bool(self.rand_p < self.p)
+        if active:
+            if self.no_noise:
+                torch.randn(n, c, 1, 1, device=dev); torch.randn(n, c, 1, 1, device=dev)     # drawn and unused, as in the reference
+            if self.noise_learnable:
+                nn.init.normal_(self.gamma_noise)
+                nn.init.normal_(self.beta_noise)
+            if self.mix_style:
+                if self.always_use_beta:
+                    mix = torch.distributions.Beta(self.alpha, self.alpha).sample((n, 1, 1, 1)).to(dev)
+                else:
+                    mix = torch.rand(n, 1, 1, 1, dtype=torch.float32, device=dev)
+                self.lmda.copy_(mix.float())
+        self._redraw_batch_std = True            # the next forward recomputes gamma_std / beta_std into the same buffers
+        st = self._fused_step
+        if st is not None:
+            for t in (st.gamma_m, st.gamma_v, st.beta_m, st.beta_v, st.lmda_m, st.lmda_v, st.step_dev):
+                t.zero_()
+        return active
+
     def reset(self):
         """Re-draw perm / rand_p / parameters and drop the cached batch statistics.
         As in the reference this creates NEW Parameter objects (an optimizer built earlier

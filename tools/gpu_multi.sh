@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=index,name --format=csv | tee $OUT/gpus.txt
 echo "== nhwc + fused tests"; timeout 900 python -m pytest tests -m gpu -q --maxfail=20 -k "nhwc or fused or golden" 2>&1 | tail -8 | tee $OUT/pytest_sel.txt
 echo "== distributed parity (NCCL, $NG ranks)"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29541 \
-    tools/dist_parity.py 2>&1 | tail -12 | tee $OUT/dist_parity.txt
+    tests/dist_parity.py 2>&1 | tail -12 | tee $OUT/dist_parity.txt
 for n in 1 $NG; do
   echo "== bench --gpus $n"
   if [ $n -eq 1 ]; then
