@@ -46,6 +46,8 @@ def workload_config(n_gpus: int) -> dict:
         "per_gpu_batch": s["N"], "global_batch": s["N"] * n_gpus, "channels": s["C"], "height": s["H"], "width": s["W"],
         "layout": "NCHW", "parallelism": f"dp{n_gpus}" + ("+allgather(mu,sig)" if n_gpus > 1 else ""),
         "l2_policy": "working set 1.03 GB per GPU (x, y, dy, dx of 257 MB each) >> 126 MB L2; no explicit flush",
+        "execution": ("eager module path" if os.environ.get("BENCH_EAGER", "0") == "1" else
+                      "GraphedLayerStep: two CUDA graphs per step (forward | backward + fused Adam), replayed"),
     }
 
 
@@ -176,7 +178,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from maxstyle_b200 import MaxStyle, FusedStyleOptimizer, GlobalBatchMaxStyle
+    from maxstyle_b200 import MaxStyle, FusedStyleOptimizer, GlobalBatchMaxStyle, GraphedLayerStep
     from maxstyle_b200 import functional as F
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -205,12 +207,28 @@ def main():
     x = (torch.randn(n, c, h, w, device=dev, generator=gen) * 1.5 + 0.25).requires_grad_(True)
     dy = torch.randn(n, c, h, w, device=dev, generator=gen)
 
+    # The step is issued through the package's graphed entry point (maxstyle_b200.GraphedLayerStep): the same C-ABI calls
+    # the module's forward / backward make, captured once into two CUDA graphs (forward | backward + fused step) over the
+    # resident x / dy and replayed -- the eager module path costs 190-330 us of host work per step, more than the kernels.
+    # BENCH_EAGER=1 times the eager module path (layer(x); y.backward(dy); opt.step()) instead.
+    eager = os.environ.get("BENCH_EAGER", "0") == "1"
+    gstep = None if eager else GraphedLayerStep(layer, x.detach(), dy)
+
+    def fwd():
+        if eager:
+            return layer(x)
+        return gstep.forward()
+
+    def bwd(y):
+        if eager:
+            x.grad = None
+            y.backward(dy)
+            opt.step()
+        else:
+            gstep.backward()
+
     def step():
-        y = layer(x)
-        x.grad = None
-        y.backward(dy)
-        opt.step()
-        return y
+        bwd(fwd())
 
     def barrier():
         if world > 1:
@@ -226,40 +244,21 @@ def main():
         sampler.start()
     t_region0 = time.perf_counter()
     # ---- timed region: exactly K steps, CUDA events on the launching (current) stream ------
-    # Two events per step bracket the dominant kernel (the backward sweep) for the roofline line; set
-    # BENCH_INNER_EVENTS=0 to time the K steps with the begin/end events only.
-    inner = os.environ.get("BENCH_INNER_EVENTS", "1") != "0"
+    # Two events per step bracket the dominant kernel (the backward sweep) for the roofline line.
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = F.launches.kernels
     barrier()
     e_begin.record()
-    if inner:
-        for i in range(K):
-            y = layer(x)
-            x.grad = None
-            ev[i][0].record()
-            y.backward(dy)
-            ev[i][1].record()
-            opt.step()
-    else:
-        for i in range(K):
-            y = layer(x)
-            x.grad = None
-            y.backward(dy)
-            opt.step()
+    for i in range(K):
+        y = fwd()
+        ev[i][0].record()
+        bwd(y)
+        ev[i][1].record()
     e_end.record()
     barrier()
     launches = F.launches.kernels - launches0
     total_ms = e_begin.elapsed_time(e_end)
-    if not inner:                        # separate instrumented pass (not part of `value`)
-        for i in range(K):
-            y = layer(x)
-            x.grad = None
-            ev[i][0].record()
-            y.backward(dy)
-            ev[i][1].record()
-        barrier()
     bwd_ms = statistics.fmean(ev[i][0].elapsed_time(ev[i][1]) for i in range(K))
     fwd_ms = total_ms / K - bwd_ms
     # keep the same load running (untimed) long enough for nvidia-smi's 100 ms sampling to see it

@@ -6,7 +6,8 @@ from .mixstyle import MixStyle
 from .distributed import GlobalBatchMaxStyle, StyleTableExchange
 from .host_pipeline import HostStepPipeline, HostStepResult
 from .executor import StyleLoopExecutor
+from .graphed import GraphedLayerStep
 
 __all__ = ["MaxStyle", "MixStyle", "FusedStyleOptimizer", "GlobalBatchMaxStyle", "StyleTableExchange",
-           "HostStepPipeline", "HostStepResult", "StyleLoopExecutor"]
+           "HostStepPipeline", "HostStepResult", "StyleLoopExecutor", "GraphedLayerStep"]
 __version__ = "0.1.0"

@@ -128,3 +128,32 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
                 assert "/root/reference" not in src, f
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(always_use_beta=True), dict(no_noise=True, noise_learnable=False),
+                                dict(mix_style=False), dict(mix_learnable=False)])
+def test_reinit_in_place_draws_like_a_fresh_construction(kw):
+    """MaxStyle.reinit_() (used by StyleLoopExecutor for CUDA-graph replay) must consume the generators exactly like
+    init_parameters() and write the same values -- into the SAME tensors."""
+    import torch
+    from maxstyle_b200 import MaxStyle
+    n, c = 7, 5
+    torch.manual_seed(99)
+    m = MaxStyle(n, c, p=2.0, use_gpu=False, **kw)       # p = 2: storage for the active case
+    m.p = 0.5
+    ptrs = [t.data_ptr() for t in (m.gamma_noise, m.beta_noise, m.lmda)]
+    for seed in range(8):
+        torch.manual_seed(seed)
+        active = m.reinit_()
+        after = float(torch.rand(1))
+        torch.manual_seed(seed)
+        f = MaxStyle(n, c, p=0.5, use_gpu=False, **kw)
+        assert float(torch.rand(1)) == after, "generator consumed differently"
+        assert torch.equal(m.perm, f.perm) and torch.equal(m.rand_p, f.rand_p)
+        assert active == bool(f.rand_p < f.p)
+        if active:
+            if kw.get("noise_learnable", True):
+                assert torch.equal(m.gamma_noise.detach(), f.gamma_noise.detach()) and torch.equal(m.beta_noise.detach(), f.beta_noise.detach())
+            if kw.get("mix_style", True):
+                assert torch.equal(m.lmda.detach(), f.lmda.detach())
+        assert [t.data_ptr() for t in (m.gamma_noise, m.beta_noise, m.lmda)] == ptrs, "reinit_ must not re-allocate"
