@@ -349,9 +349,24 @@ def main():
                 "sample": f"{res['iters']} timed steps (best-of) of the full batch {n}x{c}x{h}x{w} fp32 fwd+bwd+Adam step "
                           "of the reference's ATen op chain (oracle/torch_port.py), 1 warm-up",
                 "ms_per_step": res["seconds_per_step"] * 1e3}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that hold captured NCCL kernels must be gone before the communicator is torn down (a live graph made
+        # destroy_process_group() hang on the 2-GPU box); release them, give the teardown 10 s, then leave without running
+        # any more destructors.
+        import gc
+        import threading
+        barrier()
+        if gstep is not None:
+            gstep.close()
+        gstep = None
+        gc.collect()
+        torch.cuda.synchronize()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(10.0)
+        sys.stdout.flush()
+        os._exit(0)
     return 0
 
 

@@ -104,6 +104,12 @@ class GraphedLayerStep:
                        layer.gamma_std, layer.beta_std, self.flags, self.ws, need_dx=self.dx is not None,
                        need_noise_grad=self.keep, need_mix_grad=self.keep, step=self.step, dx_out=self.dx, grads_out=self.grads)
 
+    def close(self):
+        """Release the two graphs.  With a distributed layer they hold captured NCCL kernels: call this (after a device
+        synchronize) BEFORE `torch.distributed.destroy_process_group()`, which otherwise waits for them."""
+        self.fwd_graph = None
+        self.bwd_graph = None
+
     def forward(self) -> torch.Tensor:
         self.fwd_graph.replay()
         F.launches.kernels += self.fwd_kernels
