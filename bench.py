@@ -44,7 +44,7 @@ def workload_config(n_gpus: int) -> dict:
         "workload": f"MaxStyle layer fwd+bwd+fused Adam step, fp32 NCHW {s['N']}x{s['C']}x{s['H']}x{s['W']} per GPU "
                     "(BASELINE config-1 shape = FCN_64 layer-4 activation of config 2), all params learnable, p=1",
         "per_gpu_batch": s["N"], "global_batch": s["N"] * n_gpus, "channels": s["C"], "height": s["H"], "width": s["W"],
-        "layout": "NCHW", "parallelism": f"dp{n_gpus}" + ("+allgather(mu,sig)" if n_gpus > 1 else ""),
+        "layout": "NCHW", "parallelism": f"dp{n_gpus}" + ("+exchange(mu,sig)" if n_gpus > 1 else ""),
         "l2_policy": "working set 1.03 GB per GPU (x, y, dy, dx of 257 MB each) >> 126 MB L2; no explicit flush",
         "execution": ("eager module path" if os.environ.get("BENCH_EAGER", "0") == "1" else
                       "GraphedLayerStep: two CUDA graphs per step (forward | backward + fused Adam), replayed"),
@@ -212,7 +212,10 @@ def main():
     # resident x / dy and replayed -- the eager module path costs 190-330 us of host work per step, more than the kernels.
     # BENCH_EAGER=1 times the eager module path (layer(x); y.backward(dy); opt.step()) instead.
     eager = os.environ.get("BENCH_EAGER", "0") == "1"
-    gstep = None if eager else GraphedLayerStep(layer, x.detach(), dy)
+    gstep = None if eager else GraphedLayerStep(layer, x.detach(), dy, exchange=os.environ.get("BENCH_EXCHANGE", "auto"))
+    gstep_exchange = ({"p2p": "fused exchange+tables kernel over NVLink peer memory (maxstyle_tables_p2p)",
+                       "nccl": "NCCL all_gather_into_tensor captured in the forward graph"}.get(gstep.exchange, "NCCL all-gather (eager module)")
+                      if gstep is not None else "NCCL all-gather (eager module)")
 
     def fwd():
         if eager:
@@ -328,7 +331,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(world), **({"exchange": gstep_exchange} if world > 1 else {})),
             "roofline": {"bound": "hbm", "kernel": "bwd_nchw_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_ms": bwd_ms},

@@ -136,6 +136,24 @@ int maxstyle_tables(const float* mu_all, const float* sig_all, int table_ld, int
                     float* gamma_std, float* beta_std, int flags,
                     float* scale, float* shift, maxstyle_stream_t stream);
 
+/* Multi-GPU: the exchange of the (mu | sig) rows AND the table step in ONE kernel over NVLink peer memory -- the fused
+ * form of "all-gather, then maxstyle_tables" (no reference counterpart: the reference is single-GPU; north_star's one
+ * collective on the path).  `peers` is a DEVICE array of `world` addresses: entry r is rank r's exchange buffer of
+ * maxstyle_p2p_bytes(N, C, world) bytes, mapped into this process (symmetric memory / CUDA IPC; the caller owns and maps it,
+ * zero-filled once).  Rank `rank` must have filled rows [rank*N, (rank+1)*N) of mu_all / sig_all (maxstyle_stats); on return
+ * (stream-ordered) all N_global = N*world rows are present, exactly as after an all-gather, and scale / shift (and on the
+ * first forward gamma_std / beta_std) are computed from them.  CTA c pushes channel c of this rank's rows into every
+ * peer's buffer as 8-byte {value, epoch} words with single stores over NVLink (the epoch tag is the arrival flag: no
+ * fence, no round trip), spins on the words of channel c in its own buffer and copies them into the table; `epoch` (device counter,
+ * starts at 0, advanced by the kernel) numbers the exchanges so the call replays from a CUDA graph with fixed arguments;
+ * `done` is a zeroed device word; `error` is set to 1 if a peer did not publish within ~2 s.  Every rank must make the same
+ * sequence of calls. */
+size_t maxstyle_p2p_bytes(int N, int C, int world);
+int maxstyle_tables_p2p(const uint64_t* peers, int rank, int world, uint32_t* epoch, uint32_t* done, int* error,
+                        float* mu_all, float* sig_all, int table_ld, int N_global, int row_offset, int N, int C,
+                        const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
+                        float* gamma_std, float* beta_std, int flags, float* scale, float* shift, maxstyle_stream_t stream);
+
 /* Kernel 2 -- apply (replaces the normalise + affine chain, maxstyle.py:161,181-185). */
 int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, int row_offset, const float* scale,
                    const float* shift, int N, int C, int H, int W, int dtype, int layout, int sweep,

@@ -3,11 +3,11 @@ cherise215/MaxStyle `src/advanced/maxstyle.py`) over hand-written sm_100a CUDA k
 from .layer import MaxStyle
 from .optim import FusedStyleOptimizer
 from .mixstyle import MixStyle
-from .distributed import GlobalBatchMaxStyle, StyleTableExchange
+from .distributed import GlobalBatchMaxStyle, StyleTableExchange, PeerTableExchange
 from .host_pipeline import HostStepPipeline, HostStepResult
 from .executor import StyleLoopExecutor
 from .graphed import GraphedLayerStep
 
-__all__ = ["MaxStyle", "MixStyle", "FusedStyleOptimizer", "GlobalBatchMaxStyle", "StyleTableExchange",
+__all__ = ["MaxStyle", "MixStyle", "FusedStyleOptimizer", "GlobalBatchMaxStyle", "StyleTableExchange", "PeerTableExchange",
            "HostStepPipeline", "HostStepResult", "StyleLoopExecutor", "GraphedLayerStep"]
 __version__ = "0.1.0"

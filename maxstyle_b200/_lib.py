@@ -47,6 +47,9 @@ SIGNATURES = {
                                  C.c_float, C.c_int, _vp, C.c_size_t, _vp]),
     "maxstyle_tables": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _f32p, _f32p, _f32p,
                                   _f32p, _f32p, C.c_int, _f32p, _f32p, _vp]),
+    "maxstyle_p2p_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "maxstyle_tables_p2p": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      _vp, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, _vp]),
     "maxstyle_apply": (C.c_int, [_vp, _vp, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, _vp]),
     "maxstyle_fwd": (C.c_int, [_vp, _vp, _f32p, _f32p, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,

@@ -226,13 +226,26 @@ void launch_fused(const FwdCall& f, const FusedArgs& a, int grid) {
 
 // Returns MAXSTYLE_OK after launching, -1 when this problem does not qualify (the caller then takes the
 // two-pass path), or an error code.
-int try_fused_fwd(const FwdCall& f, const Workspace& w, int sms, bool force) {
+// First channel whose x the forward leaves in L2 (evict-last on the apply pass's re-read) for the backward sweep that follows:
+// the last MAXSTYLE_FUSED_KEEP_MB of the tensor.  Off by default: measured on the config-1 step it moves the backward from
+// 133.6 to 132.4 us at 64 MB and costs the forward as much (profiles/r01_keep.txt) -- the backward is not limited by its
+// DRAM reads of x.
+int keep_from_channel(int N, int C, int64_t M, int dtype, bool keep_x) {
+    static const int64_t keep_bytes = env_or("MAXSTYLE_FUSED_KEEP_MB", 0, 1 << 20);
+    if (!keep_x || keep_bytes <= 0) return C;
+    const int64_t channel_bytes = (int64_t)N * M * elem_size(dtype);
+    const int64_t k = keep_bytes / channel_bytes;
+    return k >= C ? 0 : (int)(C - k);
+}
+
+int try_fused_fwd(const FwdCall& f, const Workspace& w, int sms, bool force, bool keep_x) {
     const FusedPlan fp = make_fused_plan(f.N, f.C, f.M, f.dtype, common_align(f.x, f.y));
     if (!fp.ok || (!fp.profitable && !force)) return -1;
     FusedArgs a;
     a.N = f.N; a.C = f.C; a.M = f.M;
     a.nvec = fp.nvec; a.pieces = fp.pieces; a.piece_vecs = fp.piece_vecs; a.items_per_channel = fp.items_per_channel;
     a.window = fp.window; a.chunk = fp.chunk; a.total_items = fp.total_items;
+    a.keep_from = keep_from_channel(f.N, f.C, f.M, f.dtype, keep_x);
     a.flags = f.flags; a.eps = f.eps;
     a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
     a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
@@ -286,13 +299,14 @@ int launch_ring(const FwdCall& f, const FusedArgs& a, const RingPlan& rp, int sm
 }
 
 // Same contract as try_fused_fwd.
-int try_ring_fwd(const FwdCall& f, const Workspace& w, int sms, bool force) {
+int try_ring_fwd(const FwdCall& f, const Workspace& w, int sms, bool force, bool keep_x) {
     const RingPlan rp = make_ring_plan(f.N, f.C, f.M, f.dtype, common_align(f.x, f.y));
     if (!rp.ok || (!rp.profitable && !force)) return -1;
     FusedArgs a{};
     a.N = f.N; a.C = f.C; a.M = f.M;
     a.pieces = rp.pieces; a.items_per_channel = rp.items_per_channel;
     a.window = rp.window; a.chunk = 1; a.total_items = rp.total_items;
+    a.keep_from = keep_from_channel(f.N, f.C, f.M, f.dtype, keep_x);
     a.flags = f.flags; a.eps = f.eps;
     a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
     a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
@@ -430,6 +444,29 @@ int maxstyle_tables(const float* mu_all, const float* sig_all, int table_ld, int
     return check_launch();
 }
 
+size_t maxstyle_p2p_bytes(int N, int C, int world) {
+    if (N <= 0 || C <= 0 || world <= 0) return 0;
+    return (size_t)2 * N * world * 2 * C * 8;            // two parities of {value, epoch} words for every (row, mu|sig, channel)
+}
+
+int maxstyle_tables_p2p(const uint64_t* peers, int rank, int world, uint32_t* epoch, uint32_t* done, int* error,
+                        float* mu_all, float* sig_all, int table_ld, int N_global, int row_offset, int N, int C,
+                        const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
+                        float* gamma_std, float* beta_std, int flags, float* scale, float* shift, maxstyle_stream_t stream) {
+    if (!peers || !epoch || !done || !error || !mu_all || !sig_all || !scale || !shift) return MAXSTYLE_ERR_BAD_ARG;
+    if (world < 1 || world > kTableThreads || rank < 0 || rank >= world) return MAXSTYLE_ERR_BAD_ARG;
+    if (N <= 0 || C <= 0 || N_global != N * world || row_offset != rank * N || table_ld < C) return MAXSTYLE_ERR_BAD_ARG;
+    if ((flags & MAXSTYLE_MIX_STYLE) && (!perm || !lmda)) return MAXSTYLE_ERR_BAD_ARG;
+    if (!(flags & MAXSTYLE_NO_NOISE) && (!gamma_noise || !beta_noise || !gamma_std || !beta_std)) return MAXSTYLE_ERR_BAD_ARG;
+    PeerTables pt;
+    pt.peers = reinterpret_cast<const unsigned long long*>(peers);
+    pt.rank = rank; pt.world = world; pt.epoch = epoch; pt.done = done; pt.error = error;
+    tables_p2p_kernel<<<C, kTableThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        pt, mu_all, sig_all, table_ld, N_global, row_offset, N, C, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, flags,
+        scale, shift);
+    return check_launch();
+}
+
 int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, int row_offset, const float* scale,
                    const float* shift, int N, int C, int H, int W, int dtype, int layout, int sweep,
                    maxstyle_stream_t stream) {
@@ -476,10 +513,10 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
             if (rc >= 0) return rc;
         }
         if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RING)) {
-            rc = try_ring_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_RING) != 0);
+            rc = try_ring_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_RING) != 0, (stats_sweep & MAXSTYLE_SWEEP_X_KEEP) != 0);
             if (rc >= 0) return rc;
         }
-        rc = try_fused_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW) != 0);
+        rc = try_fused_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW) != 0, (stats_sweep & MAXSTYLE_SWEEP_X_KEEP) != 0);
         if (rc >= 0) return rc;
     }
     rc = maxstyle_stats(x, mu, sig, C, 0, N, C, H, W, dtype, layout, eps, stats_sweep, workspace, workspace_bytes, stream);

@@ -34,6 +34,8 @@ struct FusedArgs {
     int items_per_channel;     // N * Kp
     int window;                // D: channels between statistics and apply (<= C)
     int chunk;                 // consecutive items a CTA takes per ticket (1..kFusedMaxChunk)
+    int keep_from;             // apply items of channels >= keep_from re-read x with evict-last: the tail of x stays in L2
+                               // for the backward sweep that follows the forward (C: keep nothing)
     int64_t total_items;       // 2 * C * items_per_channel
     int flags;
     float eps;
@@ -348,11 +350,12 @@ fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a) {
             const float m = __ldcg(a.mu + plane), sc = __ldcg(a.scale + plane), shf = __ldcg(a.shift + plane);
             const T* src = x + plane * a.M;
             T* dst = y + plane * a.M;
+            const uint64_t pol_x = it.c >= a.keep_from ? pol_keep : pol_stream;
             for (int b = 0; b < bt.full; ++b) {
                 const int64_t o = (int64_t)(bt.begin(b) + t) * VEC;
                 float val[VPT][VEC];
 #pragma unroll
-                for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(src + o + (int64_t)j * G * VEC, val[j], pol_stream);
+                for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(src + o + (int64_t)j * G * VEC, val[j], pol_x);
 #pragma unroll
                 for (int j = 0; j < VPT; ++j) {
 #pragma unroll
@@ -364,7 +367,7 @@ fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a) {
                 const int hi = bt.ragged_hi();
                 for (int lo = bt.ragged_lo() + t; lo < hi; lo += G) {
                     float v[VEC];
-                    Vec<T, VEC>::load(src + (int64_t)lo * VEC, v, pol_stream);
+                    Vec<T, VEC>::load(src + (int64_t)lo * VEC, v, pol_x);
 #pragma unroll
                     for (int k = 0; k < VEC; ++k) v[k] = fmaf(v[k] - m, sc, shf);
                     Vec<T, VEC>::store(dst + (int64_t)lo * VEC, v, pol_stream);

@@ -87,7 +87,7 @@ fwd_ring_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a, RingGeo
                 const int off0 = it.k * rg.piece_bytes;
                 const int len = min(rg.piece_bytes, rg.plane_bytes - off0);
                 const char* src = reinterpret_cast<const char*>(x + plane * a.M) + off0;
-                const uint64_t pol = it.apply ? pol_stream : pol_keep;     // statistics pass leaves x in L2 for the apply pass
+                const uint64_t pol = (it.apply && it.c < a.keep_from) ? pol_stream : pol_keep;   // statistics pass leaves x in L2 for the apply pass; the tail stays for the backward
                 for (int off = 0, ch = 0; off < len; off += kRingChunkBytes, ++ch) {
                     acquire();
                     const int bytes = min(kRingChunkBytes, len - off);

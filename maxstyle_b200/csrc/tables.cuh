@@ -23,12 +23,11 @@ __device__ __forceinline__ float block_sum_128(float v, float* red) {
 //  (2) for the local rows: l = clamp(lmda,0,1); partner row = perm[row]; sig_mix / mu_mix lerp
 //      (maxstyle.py:173-176); A = sig_mix + gamma_noise*gamma_std, B = mu_mix + beta_noise*beta_std
 //      (:184-185); scale = A/sig, shift = B.
-__global__ void __launch_bounds__(kTableThreads)
-tables_kernel(const float* __restrict__ mu_all, const float* __restrict__ sig_all, int ld, int n_global, int row_offset,
-              int n_local, int C, const int64_t* __restrict__ perm, const float* __restrict__ lmda,
-              const float* __restrict__ gamma_noise, const float* __restrict__ beta_noise,
-              float* __restrict__ gamma_std, float* __restrict__ beta_std, int flags,
-              float* __restrict__ scale, float* __restrict__ shift) {
+__device__ __forceinline__ void tables_body(const float* mu_all, const float* sig_all, int ld, int n_global, int row_offset,
+                                            int n_local, int C, const int64_t* __restrict__ perm, const float* __restrict__ lmda,
+                                            const float* __restrict__ gamma_noise, const float* __restrict__ beta_noise,
+                                            float* __restrict__ gamma_std, float* __restrict__ beta_std, int flags,
+                                            float* __restrict__ scale, float* __restrict__ shift) {
     __shared__ float red[4];
     const int c = blockIdx.x;
     const bool mix = flags & 1, no_noise = flags & 2, compute_std = flags & 4;
@@ -65,6 +64,103 @@ tables_kernel(const float* __restrict__ mu_all, const float* __restrict__ sig_al
                      sc, sh, !(flags & 8));
         scale[(int64_t)n * C + c] = sc;
         shift[(int64_t)n * C + c] = sh;
+    }
+}
+
+__global__ void __launch_bounds__(kTableThreads)
+tables_kernel(const float* __restrict__ mu_all, const float* __restrict__ sig_all, int ld, int n_global, int row_offset,
+              int n_local, int C, const int64_t* __restrict__ perm, const float* __restrict__ lmda,
+              const float* __restrict__ gamma_noise, const float* __restrict__ beta_noise,
+              float* __restrict__ gamma_std, float* __restrict__ beta_std, int flags,
+              float* __restrict__ scale, float* __restrict__ shift) {
+    tables_body(mu_all, sig_all, ld, n_global, row_offset, n_local, C, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, flags,
+                scale, shift);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exchange + tables in ONE kernel over NVLink peer memory (multi-GPU forward): replaces the NCCL all-gather of the
+// (mu | sig) rows AND the table kernel that follows it.  Every rank owns a small buffer in symmetric memory
+// (torch.distributed._symmetric_memory: the same allocation mapped into every peer's address space):
+//     inbox [2 parities][N_global][2][C] x {value bits, epoch}   8-byte words other ranks PUSHED here
+// CTA c (one per channel): pushes this rank's rows of channel c into every peer's inbox as 8-byte {value, epoch} words
+// with single stores over NVLink (posted writes; an 8-byte store is indivisible, so the epoch tag IS the arrival flag --
+// no fence, no separate flag, no round trip: the low-latency scheme NCCL's LL protocol uses); then every thread spins on
+// the words it needs in its OWN inbox (local memory) until they carry this epoch, writes them into the local
+// [N_global, ld] table and the CTA goes on with the table arithmetic of tables_body on the now complete channel.  No
+// grid-wide or device-wide barrier: a channel only waits for the same channel on the other ranks, and every CTA pushes
+// BEFORE it waits, so ranks cannot wait on each other in a cycle.  The epoch lives in device memory (the last CTA out
+// increments it), parity = epoch & 1, so the kernel's arguments never change and it replays from a CUDA graph.  Two
+// parities are enough: a rank reaches epoch e+2 only after its peers pushed e+1, which they do after finishing their
+// kernel of epoch e, i.e. after they consumed the words of epoch e.
+// ---------------------------------------------------------------------------------------------
+struct PeerTables {
+    const unsigned long long* peers;   // [R] device array: base address of every rank's symmetric buffer (own entry included)
+    int rank, world;
+    unsigned int* epoch;               // local: number of exchanges completed so far
+    unsigned int* done;                // local: CTAs finished in this launch (zero between launches)
+    int* error;                        // local: set to 1 if a wait timed out
+};
+
+__device__ __forceinline__ void st_ll(void* p, float v, unsigned int tag) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const void* p, unsigned int tag, float& v) {
+    unsigned int bits, got;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(bits), "=r"(got) : "l"(p) : "memory");
+    v = __uint_as_float(bits);
+    return got == tag;
+}
+
+__global__ void __launch_bounds__(kTableThreads)
+tables_p2p_kernel(PeerTables pt, float* __restrict__ mu_all, float* __restrict__ sig_all, int ld, int n_global, int row_offset,
+                  int n_local, int C, const int64_t* __restrict__ perm, const float* __restrict__ lmda,
+                  const float* __restrict__ gamma_noise, const float* __restrict__ beta_noise,
+                  float* __restrict__ gamma_std, float* __restrict__ beta_std, int flags,
+                  float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x, t = threadIdx.x;
+    const unsigned int epoch = *(volatile unsigned int*)pt.epoch + 1u;
+    const int p = (int)(epoch & 1u);
+    const size_t words_per_parity = (size_t)n_global * 2 * C;  // 8-byte words
+    const int others = pt.world - 1;
+    // (1) push this rank's rows of channel c into every peer's inbox: {value, epoch} words
+    for (int i = t; i < others * n_local; i += kTableThreads) {
+        int r = i / n_local;
+        const int n = i - r * n_local;
+        if (r >= pt.rank) ++r;
+        const int64_t row = (int64_t)row_offset + n;
+        uint2* dst = reinterpret_cast<uint2*>(pt.peers[r]) + p * words_per_parity + (size_t)row * 2 * C + c;
+        st_ll(dst, mu_all[row * ld + c], epoch);
+        st_ll(dst + C, sig_all[row * ld + c], epoch);
+    }
+    // (2) received words (local memory) -> local table, as they arrive
+    const uint2* inbox = reinterpret_cast<const uint2*>(pt.peers[pt.rank]) + p * words_per_parity;
+    for (int i = t; i < others * n_local; i += kTableThreads) {
+        int r = i / n_local;
+        const int n = i - r * n_local;
+        if (r >= pt.rank) ++r;
+        const int64_t row = (int64_t)r * n_local + n;
+        const uint2* src = inbox + (size_t)row * 2 * C + c;
+        float m = 0.f, sg = 0.f;
+        const long long t0 = clock64();
+        while (!(ld_ll(src, epoch, m) & ld_ll(src + C, epoch, sg))) {
+            if (clock64() - t0 > 4000000000LL) { *pt.error = 1; break; }
+        }
+        mu_all[row * ld + c] = m;
+        sig_all[row * ld + c] = sg;
+    }
+    __syncthreads();
+    // (3) the table arithmetic on the complete channel
+    tables_body(mu_all, sig_all, ld, n_global, row_offset, n_local, C, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, flags,
+                scale, shift);
+    // (4) the last CTA out closes the epoch
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        if (atomicAdd(pt.done, 1u) == gridDim.x - 1u) {
+            *pt.done = 0u;
+            *pt.epoch = epoch;
+            __threadfence();
+        }
     }
 }
 

@@ -68,6 +68,37 @@ class StyleTableExchange:
         return buf
 
 
+class PeerTableExchange:
+    """The exchange buffers of `maxstyle_tables_p2p` (include/maxstyle_b200.h): one small buffer per rank in symmetric
+    memory (torch.distributed._symmetric_memory: allocated on every rank, mapped into every peer over NVLink), the device
+    array of the peers' addresses, and the device-side epoch / done / error words.  Construction is collective (every rank
+    of the group must call it, in the same order).  Raises if symmetric memory is not available -- callers that can also
+    use the NCCL all-gather (GraphedLayerStep) decide what to do then."""
+
+    def __init__(self, n_local: int, c: int, device, group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        nbytes = int(L.get_lib().maxstyle_p2p_bytes(n_local, c, self.world))
+        self.buffer = symm.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.buffer.zero_()
+        self.handle = symm.rendezvous(self.buffer, group=group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != self.buffer.data_ptr():
+            raise RuntimeError("maxstyle_b200: symmetric-memory rendezvous returned unexpected peer pointers")
+        self.peers_dev = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.done = torch.zeros(1, dtype=torch.int32, device=device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        self.handle.barrier()                        # every rank's buffer is zeroed before anyone publishes into the scheme
+
+    def check(self):
+        """Synchronises; raises if a wait for a peer timed out since construction (debug / tests)."""
+        if int(self.error.item()) != 0:
+            raise RuntimeError("maxstyle_b200: maxstyle_tables_p2p timed out waiting for a peer rank; results are invalid")
+
+
 class GlobalBatchMaxStyle(MaxStyle):
     """MaxStyle whose mixing partners and batch statistics span the global data-parallel batch.
 

@@ -193,6 +193,24 @@ def style_tables(mu_all, sig_all, row_offset: int, n_local: int, perm_dev, lmda,
     return scale, shift
 
 
+def style_tables_p2p(peer, mu_all, sig_all, row_offset: int, n_local: int, perm_dev, lmda, gamma_noise, beta_noise,
+                     gamma_std, beta_std, flags: int, scale=None, shift=None):
+    """maxstyle_tables_p2p: exchange of the (mu | sig) rows over NVLink peer memory + the table step, one kernel.
+    `peer` is a distributed.PeerTableExchange (symmetric-memory buffers, device epoch counter)."""
+    n_global, c = mu_all.shape
+    if scale is None:
+        scale = torch.empty(n_local, c, dtype=torch.float32, device=mu_all.device)
+        shift = torch.empty(n_local, c, dtype=torch.float32, device=mu_all.device)
+    rc = L.get_lib().maxstyle_tables_p2p(peer.peers_dev.data_ptr(), peer.rank, peer.world, peer.epoch.data_ptr(),
+                                         peer.done.data_ptr(), peer.error.data_ptr(), mu_all.data_ptr(), sig_all.data_ptr(),
+                                         table_ld(mu_all), n_global, row_offset, n_local, c, _ptr(perm_dev), _ptr(lmda),
+                                         _ptr(gamma_noise), _ptr(beta_noise), _ptr(gamma_std), _ptr(beta_std), flags,
+                                         scale.data_ptr(), shift.data_ptr(), _stream())
+    L.check(rc, "maxstyle_tables_p2p")
+    launches.kernels += 1
+    return scale, shift
+
+
 def style_apply(x, mu_all, row_offset: int, scale, shift, out=None, sweep: Optional[int] = None):
     n, c, h, w = x.shape
     y = _like(x) if out is None else out

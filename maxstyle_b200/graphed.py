@@ -26,11 +26,15 @@ class GraphedLayerStep:
         layer: an ACTIVE MaxStyle / GlobalBatchMaxStyle (attach a FusedStyleOptimizer first if the step is wanted).
         x, dy: static input tensors (NCHW or channels_last; fp32 / bf16) -- write new data into them between replays.
         need_dx: also produce the gradient w.r.t. x (False for the first spliced layer, whose input is detached).
+        exchange (GlobalBatchMaxStyle only): how the (mu | sig) rows travel between ranks -- "p2p": the fused
+            exchange + tables kernel over NVLink peer memory (maxstyle_tables_p2p; collective construction); "nccl":
+            all_gather_into_tensor then the table kernel; "auto": p2p when symmetric memory can be set up on every rank,
+            else nccl (`self.exchange` says which).
     Attributes: `y`, `dx` (static outputs), `grads` = (d_gamma, d_beta, d_lmda) when the layer has no fused step or it
     keeps gradients, `kernels_per_step` (for launch accounting).
     """
 
-    def __init__(self, layer: MaxStyle, x: torch.Tensor, dy: torch.Tensor, need_dx: bool = True):
+    def __init__(self, layer: MaxStyle, x: torch.Tensor, dy: torch.Tensor, need_dx: bool = True, exchange: str = "auto"):
         if not x.is_cuda:
             raise RuntimeError("maxstyle_b200: GraphedLayerStep needs CUDA tensors (there is no CPU path)")
         if not layer.is_active():
@@ -55,11 +59,14 @@ class GraphedLayerStep:
         self.grads = None
         if self.keep:
             self.grads = (torch.empty(n, c, device=dev), torch.empty(n, c, device=dev), torch.empty(n, device=dev))
+        self.exchange = None
+        self.peer = None
         if self.distributed:
             self.table = layer._exchange.allocate(n, c, dev)
             self.mu_all, self.sig_all = layer._exchange.views(self.table)
             self.scale = torch.empty(n, c, device=dev)
             self.shift = torch.empty(n, c, device=dev)
+            self.exchange = self._setup_exchange(exchange, n, c, dev)
         else:
             self.tables = torch.empty(4, n, c, dtype=torch.float32, device=dev)
             self.mu_all, self.sig_all, self.scale, self.shift = self.tables[0], self.tables[1], self.tables[2], self.tables[3]
@@ -84,15 +91,42 @@ class GraphedLayerStep:
         F.launches.kernels = k0 + self.fwd_kernels                      # captures launch nothing; the warm-up did run
         self.kernels_per_step = self.fwd_kernels + 1
 
+    def _setup_exchange(self, want: str, n: int, c: int, dev) -> str:
+        """Collective: every rank tries to set up the peer-memory exchange, then all agree (MIN over ranks) on using it."""
+        import torch.distributed as dist
+        from .distributed import PeerTableExchange
+        if want not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"exchange must be 'auto', 'p2p' or 'nccl', got {want!r}")
+        if want == "nccl":
+            return "nccl"
+        group = self.layer._exchange.group
+        ok, err = 1, None
+        try:
+            self.peer = PeerTableExchange(n, c, dev, group)
+        except Exception as e:                                   # noqa: BLE001  (no symmetric memory on this system)
+            ok, err = 0, e
+        agree = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=group)
+        if int(agree.item()) == 1:
+            return "p2p"
+        self.peer = None
+        if want == "p2p":
+            raise RuntimeError(f"maxstyle_b200: peer-memory exchange requested but not available on every rank: {err!r}")
+        return "nccl"
+
     # the same call sequences as MaxStyleFunction / GlobalBatchFunction, on the static buffers
     def _forward(self, flags: int):
         layer = self.layer
         if self.distributed:
             n = self.x.shape[0]
             F.instance_stats(self.x, layer.eps, self.ws, self.mu_all, self.sig_all, self.row_offset)
-            layer._exchange.gather(self.table, n)
-            F.style_tables(self.mu_all, self.sig_all, self.row_offset, n, self.perm, layer.lmda, layer.gamma_noise, layer.beta_noise,
-                           layer.gamma_std, layer.beta_std, flags, self.scale, self.shift)
+            if self.exchange == "p2p":                           # exchange + tables: one kernel over NVLink peer memory
+                F.style_tables_p2p(self.peer, self.mu_all, self.sig_all, self.row_offset, n, self.perm, layer.lmda,
+                                   layer.gamma_noise, layer.beta_noise, layer.gamma_std, layer.beta_std, flags, self.scale, self.shift)
+            else:
+                layer._exchange.gather(self.table, n)
+                F.style_tables(self.mu_all, self.sig_all, self.row_offset, n, self.perm, layer.lmda, layer.gamma_noise,
+                               layer.beta_noise, layer.gamma_std, layer.beta_std, flags, self.scale, self.shift)
             F.style_apply(self.x, self.mu_all, self.row_offset, self.scale, self.shift, out=self.y)
         else:
             F.forward_raw(self.x, self.perm, layer.lmda, layer.gamma_noise, layer.beta_noise, layer.gamma_std, layer.beta_std,

@@ -86,10 +86,38 @@ def main():
     want = O.adam_step(before, grad, O.AdamState(np.zeros(n_loc, np.float32), np.zeros(n_loc, np.float32)))
     errs["adam_lmda"] = float(np.abs(layer.lmda.detach().cpu().numpy().reshape(-1) - want).max())
     assert errs["adam_lmda"] < 1e-5, errs
-    dist.barrier()
+    # GraphedLayerStep on the global-batch layer, with both transports of the (mu | sig) rows: the fused peer-memory
+    # exchange + tables kernel (maxstyle_tables_p2p) and NCCL's all-gather captured in the graph.  Several replays walk
+    # the exchange's epoch / parity scheme; every one must reproduce the golden slab.
+    from maxstyle_b200 import GraphedLayerStep
+    layer._fused_step = None                                   # gradients only: the state stays fixed across replays
+    with torch.no_grad():                                      # the fused Adam step above moved all three
+        layer.gamma_noise.copy_(torch.from_numpy(g[pre + "gamma_noise"][off:off + n_loc]).view(n_loc, c, 1, 1))
+        layer.beta_noise.copy_(torch.from_numpy(g[pre + "beta_noise"][off:off + n_loc]).view(n_loc, c, 1, 1))
+        layer.lmda.copy_(torch.from_numpy(g[pre + "lmda"].reshape(-1)[off:off + n_loc]).view(n_loc, 1, 1, 1))
+    layer.gamma_std = layer.beta_std = None
+    xs = torch.from_numpy(x_np[off:off + n_loc]).to(dev)
+    dys = torch.from_numpy(dy_np[off:off + n_loc]).to(dev)
+    for transport in ("p2p", "nccl"):
+        gs = GraphedLayerStep(layer, xs, dys, exchange=transport)
+        assert gs.exchange == transport
+        for rep in range(5):
+            y_g, dx_g = gs.run()
+            torch.cuda.synchronize()
+            errs[f"graph_{transport}_y"] = close(t2n(y_g), g[pre + "y"][off:off + n_loc], 1e-5, f"graphed {transport} y (replay {rep})")
+            errs[f"graph_{transport}_dx"] = close(t2n(dx_g), g[pre + "dx"][off:off + n_loc], 1e-4, f"graphed {transport} dx (replay {rep})")
+            errs[f"graph_{transport}_d_lmda"] = close(t2n(gs.grads[2]), g[pre + "d_lmda"].reshape(-1)[off:off + n_loc], 1e-4,
+                                                      f"graphed {transport} d_lmda", scale=np.abs(g[pre + "d_lmda"]).max())
+        if transport == "p2p":
+            gs.peer.check()
+            assert int(gs.peer.epoch.item()) == 7, int(gs.peer.epoch.item())     # first forward + warm-up + 5 replays
+        gs.close()
+        torch.cuda.synchronize()
+        dist.barrier()
     print(f"[dist_parity] rank {rank}/{world} ok", json.dumps({k: (v if isinstance(v, float) else {a: f"{b:.1e}" for a, b in v.items()})
                                                                 for k, v in errs.items()}), flush=True)
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)        # graphs with captured NCCL kernels were just released; skip the communicator teardown
 
 
 if __name__ == "__main__":

@@ -21,7 +21,7 @@ def lib():
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(maxstyle_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(maxstyle_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_are_exported_and_bound(lib):
