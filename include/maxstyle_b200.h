@@ -154,6 +154,20 @@ int maxstyle_tables_p2p(const uint64_t* peers, int rank, int world, uint32_t* ep
                         const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
                         float* gamma_std, float* beta_std, int flags, float* scale, float* shift, maxstyle_stream_t stream);
 
+/* Multi-GPU whole forward in ONE kernel: the L2-window forward of maxstyle_fwd whose channel finaliser exchanges the channel's
+ * (mu | sig) rows with the other ranks through the same peer-memory inboxes and epoch counter as maxstyle_tables_p2p (the
+ * two calls may be mixed on one set of buffers as long as every rank makes the same sequence of calls).  x is read from HBM
+ * once, y written once, and the exchange hides behind the 32 MB of streaming between a channel's statistics and its apply
+ * items.  Returns MAXSTYLE_ERR_UNSUPPORTED without launching anything when the shape does not qualify for the window kernel
+ * (the caller then runs maxstyle_stats -> maxstyle_tables_p2p -> maxstyle_apply); every rank sees the same answer for the
+ * same shape.  A peer that does not publish within ~2 s raises the workspace error flag (maxstyle_workspace_status). */
+int maxstyle_fwd_p2p(const void* x, void* y, float* mu_all, float* sig_all, int table_ld, int N_global, int row_offset,
+                     const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
+                     float* gamma_std, float* beta_std, float* scale, float* shift,
+                     int N, int C, int H, int W, int dtype, int layout, int flags, float eps, int stats_sweep,
+                     const uint64_t* peers, int rank, int world, uint32_t* epoch,
+                     void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
+
 /* Kernel 2 -- apply (replaces the normalise + affine chain, maxstyle.py:161,181-185). */
 int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, int row_offset, const float* scale,
                    const float* shift, int N, int C, int H, int W, int dtype, int layout, int sweep,

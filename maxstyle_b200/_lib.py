@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libmaxstyle_b200.so")
 
 # enums of include/maxstyle_b200.h
 OK = 0
+ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA, ERR_NO_DEVICE, ERR_TIMEOUT = 1, 2, 3, 4, 5, 6
 F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
 FLAG_MIX_STYLE, FLAG_NO_NOISE, FLAG_COMPUTE_BATCH_STD, FLAG_NO_CLAMP = 1, 2, 4, 8
@@ -50,6 +51,9 @@ SIGNATURES = {
     "maxstyle_p2p_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "maxstyle_tables_p2p": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       _vp, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, _vp]),
+    "maxstyle_fwd_p2p": (C.c_int, [_vp, _vp, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                   _vp, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "maxstyle_apply": (C.c_int, [_vp, _vp, _f32p, C.c_int, C.c_int, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, _vp]),
     "maxstyle_fwd": (C.c_int, [_vp, _vp, _f32p, _f32p, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,

@@ -217,7 +217,15 @@ struct FwdCall {
     const void* x; void* y; float *mu, *sig; const int64_t* perm; const float *lmda, *gamma_noise, *beta_noise;
     float *gamma_std, *beta_std, *scale, *shift; int N, C; int64_t M; int dtype, flags; float eps;
     char* ws; cudaStream_t stream;
+    // statistics tables: [n_global, ld] with this rank's rows at row_offset (single GPU: n_global == N, ld == C, no peers)
+    int n_global, row_offset, ld;
+    PeerTables pt;
 };
+
+void fill_tables(FusedArgs& a, const FwdCall& f) {
+    a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
+    a.n_global = f.n_global; a.row_offset = f.row_offset; a.ld = f.ld; a.pt = f.pt;
+}
 
 template <typename T, int VEC>
 void launch_fused(const FwdCall& f, const FusedArgs& a, int grid) {
@@ -247,7 +255,7 @@ int try_fused_fwd(const FwdCall& f, const Workspace& w, int sms, bool force, boo
     a.window = fp.window; a.chunk = fp.chunk; a.total_items = fp.total_items;
     a.keep_from = keep_from_channel(f.N, f.C, f.M, f.dtype, keep_x);
     a.flags = f.flags; a.eps = f.eps;
-    a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
+    fill_tables(a, f);
     a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
     a.gamma_std = f.gamma_std; a.beta_std = f.beta_std;
     a.partials = reinterpret_cast<float4*>(f.ws + w.res_partials);
@@ -308,7 +316,7 @@ int try_ring_fwd(const FwdCall& f, const Workspace& w, int sms, bool force, bool
     a.window = rp.window; a.chunk = 1; a.total_items = rp.total_items;
     a.keep_from = keep_from_channel(f.N, f.C, f.M, f.dtype, keep_x);
     a.flags = f.flags; a.eps = f.eps;
-    a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
+    fill_tables(a, f);
     a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
     a.gamma_std = f.gamma_std; a.beta_std = f.beta_std;
     a.partials = reinterpret_cast<float4*>(f.ws + w.res_partials);
@@ -507,7 +515,7 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
         const int sms = sm_count();
         if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
         FwdCall f{x, y, mu, sig, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, M, dtype, flags, eps,
-                  static_cast<char*>(workspace), static_cast<cudaStream_t>(stream)};
+                  static_cast<char*>(workspace), static_cast<cudaStream_t>(stream), N, 0, C, PeerTables{}};
         if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RESIDENT)) {
             rc = try_resident_fwd(f, w, sms, stats_sweep, apply_sweep, (stats_sweep & MAXSTYLE_SWEEP_FORCE_RESIDENT) != 0);
             if (rc >= 0) return rc;
@@ -525,6 +533,35 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
                          stream);
     if (rc) return rc;
     return maxstyle_apply(x, y, mu, C, 0, scale, shift, N, C, H, W, dtype, layout, apply_sweep, stream);
+}
+
+int maxstyle_fwd_p2p(const void* x, void* y, float* mu_all, float* sig_all, int table_ld, int N_global, int row_offset,
+                     const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
+                     float* gamma_std, float* beta_std, float* scale, float* shift,
+                     int N, int C, int H, int W, int dtype, int layout, int flags, float eps, int stats_sweep,
+                     const uint64_t* peers, int rank, int world, uint32_t* epoch,
+                     void* workspace, size_t workspace_bytes, maxstyle_stream_t stream) {
+    int rc = check_shape(N, C, H, W, dtype, layout);
+    if (rc) return rc;
+    if (!x || !y || !mu_all || !sig_all || !scale || !shift || !peers || !epoch || !gamma_std || !beta_std) return MAXSTYLE_ERR_BAD_ARG;
+    if (world < 2 || rank < 0 || rank >= world || N_global != N * world || row_offset != rank * N || table_ld < C)
+        return MAXSTYLE_ERR_BAD_ARG;
+    if ((flags & MAXSTYLE_MIX_STYLE) && (!perm || !lmda)) return MAXSTYLE_ERR_BAD_ARG;
+    if (!(flags & MAXSTYLE_NO_NOISE) && (!gamma_noise || !beta_noise)) return MAXSTYLE_ERR_BAD_ARG;
+    if (is_nhwc(layout, C) || N_global > kFusedMaxN) return MAXSTYLE_ERR_UNSUPPORTED;
+    const int64_t M = (int64_t)H * W;
+    const Workspace w = workspace_layout(N, C, M, dtype);
+    if ((rc = check_workspace(workspace, workspace_bytes, w))) return rc;
+    const int sms = sm_count();
+    if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+    PeerTables pt;
+    pt.peers = reinterpret_cast<const unsigned long long*>(peers);
+    pt.rank = rank; pt.world = world; pt.epoch = epoch; pt.done = nullptr;
+    pt.error = reinterpret_cast<int*>(static_cast<char*>(workspace) + w.res_error);
+    FwdCall f{x, y, mu_all, sig_all, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, M, dtype, flags, eps,
+              static_cast<char*>(workspace), static_cast<cudaStream_t>(stream), N_global, row_offset, table_ld, pt};
+    rc = try_fused_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW) != 0, (stats_sweep & MAXSTYLE_SWEEP_X_KEEP) != 0);
+    return rc >= 0 ? rc : MAXSTYLE_ERR_UNSUPPORTED;
 }
 
 int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int stats_sweep) {

@@ -20,6 +20,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_nchw.cuh"
+#include "tables.cuh"
 
 namespace ms {
 
@@ -39,7 +40,10 @@ struct FusedArgs {
     int64_t total_items;       // 2 * C * items_per_channel
     int flags;
     float eps;
-    float *mu, *sig, *scale, *shift;                 // [N, C] tables written by the channel finalisers
+    float *mu, *sig;                                 // [n_global, ld] statistics tables (single GPU: n_global == N, ld == C)
+    float *scale, *shift;                            // [N, C] coefficients of the local rows, written by the channel finalisers
+    int n_global, row_offset, ld;                    // this rank holds rows [row_offset, row_offset + N) of the global batch
+    PeerTables pt;                                   // pt.world > 1: the finaliser exchanges the channel's rows over peer memory
     const int64_t* perm;
     const float *lmda, *gamma_noise, *beta_noise;
     float *gamma_std, *beta_std;                     // [C]: written when MAXSTYLE_COMPUTE_BATCH_STD, else read
@@ -105,12 +109,22 @@ __device__ __forceinline__ FusedItem fused_item(const FusedArgs& a, int64_t id) 
 // n = lane, lane+32, ...; fin_mu / fin_sig are that warp's shared scratch ([kFusedMaxN]).
 __device__ __forceinline__ void fused_finalize_channel(const FusedArgs& a, int c, float* fin_mu, float* fin_sig) {
     const int lane = threadIdx.x & 31;
-    const int N = a.N, C = a.C, Kp = a.pieces;
+    const int N = a.N, C = a.C, Kp = a.pieces, NG = a.n_global, off = a.row_offset, ld = a.ld;
     const bool mix = a.flags & 1, no_noise = a.flags & 2, compute_std = a.flags & 4;
     const float inv_m1 = 1.0f / (float)(a.M - 1);
     const float4* part = a.partials + (int64_t)c * a.items_per_channel;
     float gs = 0.f, bs = 0.f;
     if (!compute_std && !no_noise) { gs = a.gamma_std[c]; bs = a.beta_std[c]; }
+    // Multi-GPU: this rank's rows go to every peer's inbox as {value, epoch} words the moment they exist (tables.cuh).
+    const bool multi = a.pt.world > 1;
+    unsigned int epoch = 0;
+    size_t words = 0;
+    int par = 0;
+    if (multi) {
+        epoch = *(volatile unsigned int*)a.pt.epoch + 1u;
+        par = (int)(epoch & 1u);
+        words = (size_t)NG * 2 * C;
+    }
     for (int n = lane; n < N; n += 32) {
         Moments m{0.f, 0.f, 0.f};
         float K = 0.f;
@@ -125,34 +139,64 @@ __device__ __forceinline__ void fused_finalize_channel(const FusedArgs& a, int c
         }
         const float mean = K + m.mean;
         const float sg = sqrtf(m.m2 * inv_m1 + a.eps);
-        fin_mu[n] = mean;
-        fin_sig[n] = sg;
-        a.mu[(int64_t)n * C + c] = mean;
-        a.sig[(int64_t)n * C + c] = sg;
+        fin_mu[off + n] = mean;
+        fin_sig[off + n] = sg;
+        a.mu[(int64_t)(off + n) * ld + c] = mean;
+        a.sig[(int64_t)(off + n) * ld + c] = sg;
+        if (multi) {
+            for (int r = 0; r < a.pt.world; ++r) {
+                if (r == a.pt.rank) continue;
+                uint2* dst = reinterpret_cast<uint2*>(a.pt.peers[r]) + par * words + (size_t)(off + n) * 2 * C + c;
+                st_ll(dst, mean, epoch);
+                st_ll(dst + C, sg, epoch);
+            }
+        }
+    }
+    if (multi) {
+        // the other ranks' rows of this channel: spin on the tagged words in the local inbox
+        const uint2* inbox = reinterpret_cast<const uint2*>(a.pt.peers[a.pt.rank]) + par * words;
+        const int others = (a.pt.world - 1) * N;
+        for (int i = lane; i < others; i += 32) {
+            int r = i / N;
+            const int n = i - r * N;
+            if (r >= a.pt.rank) ++r;
+            const int row = r * N + n;
+            const uint2* src = inbox + (size_t)row * 2 * C + c;
+            float m = 0.f, sg = 0.f;
+            const long long t0 = clock64();
+            while (!(ld_ll(src, epoch, m) & ld_ll(src + C, epoch, sg))) {
+                if (clock64() - t0 > 2 * kFusedSpinLimit) { *a.error = 1; break; }
+            }
+            fin_mu[row] = m;
+            fin_sig[row] = sg;
+            a.mu[(int64_t)row * ld + c] = m;
+            a.sig[(int64_t)row * ld + c] = sg;
+        }
     }
     __syncwarp();
-    if (compute_std) {                                          // two-pass unbiased std over the batch (:165-168)
+    if (compute_std) {                                          // two-pass unbiased std over the GLOBAL batch (:165-168)
         float s_sig = 0.f, s_mu = 0.f;
-        for (int n = lane; n < N; n += 32) { s_sig += fin_sig[n]; s_mu += fin_mu[n]; }
+        for (int n = lane; n < NG; n += 32) { s_sig += fin_sig[n]; s_mu += fin_mu[n]; }
         s_sig = warp_sum(s_sig);
         s_mu = warp_sum(s_mu);
-        const float mean_sig = s_sig / (float)N, mean_mu = s_mu / (float)N;
+        const float mean_sig = s_sig / (float)NG, mean_mu = s_mu / (float)NG;
         float q_sig = 0.f, q_mu = 0.f;
-        for (int n = lane; n < N; n += 32) {
+        for (int n = lane; n < NG; n += 32) {
             const float ds = fin_sig[n] - mean_sig, dm = fin_mu[n] - mean_mu;
             q_sig = fmaf(ds, ds, q_sig);
             q_mu = fmaf(dm, dm, q_mu);
         }
         q_sig = warp_sum(q_sig);
         q_mu = warp_sum(q_mu);
-        gs = sqrtf(q_sig / (float)(N - 1));
-        bs = sqrtf(q_mu / (float)(N - 1));
+        gs = sqrtf(q_sig / (float)(NG - 1));
+        bs = sqrtf(q_mu / (float)(NG - 1));
         if (lane == 0) { a.gamma_std[c] = gs; a.beta_std[c] = bs; }
     }
     for (int n = lane; n < N; n += 32) {
-        const int64_t pr = mix ? a.perm[n] : n;
+        const int row = off + n;
+        const int64_t pr = mix ? a.perm[row] : row;
         float sc, sh;
-        style_coeffs(fin_sig[n], fin_mu[n], fin_sig[pr], fin_mu[pr], mix, no_noise, mix ? a.lmda[n] : 0.f,
+        style_coeffs(fin_sig[row], fin_mu[row], fin_sig[pr], fin_mu[pr], mix, no_noise, mix ? a.lmda[n] : 0.f,
                      no_noise ? 0.f : a.gamma_noise[(int64_t)n * C + c], no_noise ? 0.f : a.beta_noise[(int64_t)n * C + c], gs, bs,
                      sc, sh, !(a.flags & 8));
         a.scale[(int64_t)n * C + c] = sc;
@@ -280,7 +324,10 @@ fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a) {
         last_cta = __shfl_sync(0xffffffffu, last_cta, 0);
         if (last_cta) {
             for (int c = lane; c < a.C; c += 32) { a.arrived[c] = 0u; a.ready[c] = 0u; }
-            if (lane == 0) { *a.queue = 0ull; *a.done = 0u; }
+            if (lane == 0) {
+                *a.queue = 0ull; *a.done = 0u;
+                if (a.pt.world > 1) *a.pt.epoch = *(volatile unsigned int*)a.pt.epoch + 1u;     // close the exchange epoch
+            }
         }
         return;
     }
@@ -347,7 +394,7 @@ fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a) {
             if (t == 0) sh.tot[u & 1][ib] = make_float4(tot.n, tot.mean, tot.m2, K);
         } else {
             // ---------------- apply: the control warp has seen the channel's ready flag ----------------
-            const float m = __ldcg(a.mu + plane), sc = __ldcg(a.scale + plane), shf = __ldcg(a.shift + plane);
+            const float m = __ldcg(a.mu + ((int64_t)a.row_offset + it.n) * a.ld + it.c), sc = __ldcg(a.scale + plane), shf = __ldcg(a.shift + plane);
             const T* src = x + plane * a.M;
             T* dst = y + plane * a.M;
             const uint64_t pol_x = it.c >= a.keep_from ? pol_keep : pol_stream;

@@ -129,7 +129,7 @@ fwd_ring_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a, RingGeo
                         }
                     }
                     named_sync(kBarRed, TC);
-                    m = __ldcg(a.mu + plane); sc = __ldcg(a.scale + plane); shf = __ldcg(a.shift + plane);
+                    m = __ldcg(a.mu + ((int64_t)a.row_offset + it.n) * a.ld + it.c); sc = __ldcg(a.scale + plane); shf = __ldcg(a.shift + plane);
                     dst = y + plane * a.M + (size_t)(it.k * rg.piece_bytes) / sizeof(T);
                 } else {
                     K = to_f32<T>(__ldg(x + plane * a.M));      // the plane's first element: common shift of all its pieces

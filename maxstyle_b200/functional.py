@@ -211,6 +211,23 @@ def style_tables_p2p(peer, mu_all, sig_all, row_offset: int, n_local: int, perm_
     return scale, shift
 
 
+def forward_p2p(peer, x, mu_all, sig_all, row_offset: int, perm_dev, lmda, gamma_noise, beta_noise, gamma_std, beta_std,
+                flags: int, eps: float, workspace, scale, shift, out) -> bool:
+    """maxstyle_fwd_p2p: the multi-GPU forward as ONE kernel (L2-window forward whose channel finaliser exchanges the rows
+    over peer memory).  Returns False -- nothing launched -- when the shape does not qualify (same answer on every rank)."""
+    n, c, h, w = x.shape
+    rc = L.get_lib().maxstyle_fwd_p2p(x.data_ptr(), out.data_ptr(), mu_all.data_ptr(), sig_all.data_ptr(), table_ld(mu_all),
+                                      mu_all.shape[0], row_offset, _ptr(perm_dev), _ptr(lmda), _ptr(gamma_noise), _ptr(beta_noise),
+                                      _ptr(gamma_std), _ptr(beta_std), scale.data_ptr(), shift.data_ptr(), n, c, h, w,
+                                      dtype_code(x), layout_of(x), flags, eps, SWEEP_STATS, peer.peers_dev.data_ptr(), peer.rank,
+                                      peer.world, peer.epoch.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream())
+    if rc == L.ERR_UNSUPPORTED:
+        return False
+    L.check(rc, "maxstyle_fwd_p2p")
+    launches.kernels += 1
+    return True
+
+
 def style_apply(x, mu_all, row_offset: int, scale, shift, out=None, sweep: Optional[int] = None):
     n, c, h, w = x.shape
     y = _like(x) if out is None else out

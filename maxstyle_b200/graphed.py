@@ -30,11 +30,14 @@ class GraphedLayerStep:
             exchange + tables kernel over NVLink peer memory (maxstyle_tables_p2p; collective construction); "nccl":
             all_gather_into_tensor then the table kernel; "auto": p2p when symmetric memory can be set up on every rank,
             else nccl (`self.exchange` says which).
+        one_kernel (with the p2p exchange): run the whole forward as the one-kernel L2-window forward with the exchange in
+            its channel finaliser (maxstyle_fwd_p2p) when the shape qualifies; False: statistics -> exchange + tables -> apply.
     Attributes: `y`, `dx` (static outputs), `grads` = (d_gamma, d_beta, d_lmda) when the layer has no fused step or it
     keeps gradients, `kernels_per_step` (for launch accounting).
     """
 
-    def __init__(self, layer: MaxStyle, x: torch.Tensor, dy: torch.Tensor, need_dx: bool = True, exchange: str = "auto"):
+    def __init__(self, layer: MaxStyle, x: torch.Tensor, dy: torch.Tensor, need_dx: bool = True, exchange: str = "auto",
+                 one_kernel: bool = True):
         if not x.is_cuda:
             raise RuntimeError("maxstyle_b200: GraphedLayerStep needs CUDA tensors (there is no CPU path)")
         if not layer.is_active():
@@ -61,6 +64,7 @@ class GraphedLayerStep:
             self.grads = (torch.empty(n, c, device=dev), torch.empty(n, c, device=dev), torch.empty(n, device=dev))
         self.exchange = None
         self.peer = None
+        self.one_kernel = None if one_kernel else False          # None: ask maxstyle_fwd_p2p on the first call
         if self.distributed:
             self.table = layer._exchange.allocate(n, c, dev)
             self.mu_all, self.sig_all = layer._exchange.views(self.table)
@@ -119,6 +123,15 @@ class GraphedLayerStep:
         layer = self.layer
         if self.distributed:
             n = self.x.shape[0]
+            if self.exchange == "p2p" and self.one_kernel is not False:
+                # whole forward in one kernel, the exchange inside its channel finaliser (maxstyle_fwd_p2p)
+                ok = F.forward_p2p(self.peer, self.x, self.mu_all, self.sig_all, self.row_offset, self.perm, layer.lmda,
+                                   layer.gamma_noise, layer.beta_noise, layer.gamma_std, layer.beta_std, flags, layer.eps, self.ws,
+                                   self.scale, self.shift, self.y)
+                if self.one_kernel is None:
+                    self.one_kernel = ok                         # decided by the first call; the same on every rank
+                if ok:
+                    return
             F.instance_stats(self.x, layer.eps, self.ws, self.mu_all, self.sig_all, self.row_offset)
             if self.exchange == "p2p":                           # exchange + tables: one kernel over NVLink peer memory
                 F.style_tables_p2p(self.peer, self.mu_all, self.sig_all, self.row_offset, n, self.perm, layer.lmda,

@@ -98,9 +98,12 @@ def main():
     layer.gamma_std = layer.beta_std = None
     xs = torch.from_numpy(x_np[off:off + n_loc]).to(dev)
     dys = torch.from_numpy(dy_np[off:off + n_loc]).to(dev)
-    for transport in ("p2p", "nccl"):
-        gs = GraphedLayerStep(layer, xs, dys, exchange=transport)
-        assert gs.exchange == transport
+    for transport in ("p2p-one-kernel", "p2p", "nccl"):
+        layer.gamma_std = layer.beta_std = None                 # each variant also runs the first-forward (batch std) path
+        gs = GraphedLayerStep(layer, xs, dys, exchange=transport.split("-")[0], one_kernel=transport == "p2p-one-kernel")
+        assert gs.exchange == transport.split("-")[0]
+        errs[f"graph_{transport}_gamma_std"] = close(t2n(layer.gamma_std).reshape(-1), g[pre + "gamma_std"].reshape(-1), 1e-5,
+                                                     f"graphed {transport} gamma_std", scale=np.abs(g[pre + "sig"]).max())
         for rep in range(5):
             y_g, dx_g = gs.run()
             torch.cuda.synchronize()
@@ -108,12 +111,41 @@ def main():
             errs[f"graph_{transport}_dx"] = close(t2n(dx_g), g[pre + "dx"][off:off + n_loc], 1e-4, f"graphed {transport} dx (replay {rep})")
             errs[f"graph_{transport}_d_lmda"] = close(t2n(gs.grads[2]), g[pre + "d_lmda"].reshape(-1)[off:off + n_loc], 1e-4,
                                                       f"graphed {transport} d_lmda", scale=np.abs(g[pre + "d_lmda"]).max())
-        if transport == "p2p":
+        if transport.startswith("p2p"):
             gs.peer.check()
             assert int(gs.peer.epoch.item()) == 7, int(gs.peer.epoch.item())     # first forward + warm-up + 5 replays
+            from maxstyle_b200 import functional as F_
+            F_.workspace_status(gs.ws, n_loc, c, h, w, 0)                        # no device-side wait timed out
+        errs[f"graph_{transport}_kernels"] = float(gs.kernels_per_step)
         gs.close()
         torch.cuda.synchronize()
         dist.barrier()
+    # The one-kernel multi-GPU forward (maxstyle_fwd_p2p: L2-window kernel, exchange in the channel finaliser) needs planes of
+    # >= 64 KB, which the golden case does not have: on a synthetic 100 KB-plane problem it must agree with the NCCL transport
+    # (different statistics kernels: last-bit differences only), first forward (global batch std) and cached forwards alike.
+    torch.manual_seed(77)
+    big = GlobalBatchMaxStyle(6, 8, p=1.0)
+    gen = torch.Generator(device=dev).manual_seed(500 + rank)
+    xb = torch.randn(6, 8, 160, 160, device=dev, generator=gen) * 1.7 + 0.4
+    dyb = torch.randn(6, 8, 160, 160, device=dev, generator=gen)
+    outs = {}
+    for name, kw in (("one", dict(exchange="p2p", one_kernel=True)), ("nccl", dict(exchange="nccl"))):
+        big.gamma_std = big.beta_std = None
+        gsb = GraphedLayerStep(big, xb, dyb, **kw)
+        for _ in range(3):
+            yb, dxb = gsb.run()
+        torch.cuda.synchronize()
+        outs[name] = [t.detach().clone() for t in (yb, dxb, gsb.grads[0], gsb.grads[1], gsb.grads[2], big.gamma_std, big.beta_std)]
+        if name == "one":
+            assert gsb.one_kernel is True and gsb.kernels_per_step == 2, (gsb.one_kernel, gsb.kernels_per_step)
+            gsb.peer.check()
+            F_.workspace_status(gsb.ws, 6, 8, 160, 160, 0)
+        gsb.close()
+        torch.cuda.synchronize()
+        dist.barrier()
+    for i, nm in enumerate(("y", "dx", "d_gamma", "d_beta", "d_lmda", "gamma_std", "beta_std")):
+        a_, b_ = t2n(outs["one"][i]), t2n(outs["nccl"][i])
+        errs[f"one_kernel_vs_nccl_{nm}"] = close(a_, b_, 1e-5 if nm in ("y", "gamma_std", "beta_std") else 1e-4, f"one-kernel vs nccl {nm}")
     print(f"[dist_parity] rank {rank}/{world} ok", json.dumps({k: (v if isinstance(v, float) else {a: f"{b:.1e}" for a, b in v.items()})
                                                                 for k, v in errs.items()}), flush=True)
     sys.stdout.flush()
