@@ -213,7 +213,9 @@ def main():
     # BENCH_EAGER=1 times the eager module path (layer(x); y.backward(dy); opt.step()) instead.
     eager = os.environ.get("BENCH_EAGER", "0") == "1"
     gstep = None if eager else GraphedLayerStep(layer, x.detach(), dy, exchange=os.environ.get("BENCH_EXCHANGE", "auto"))
-    gstep_exchange = ({"p2p": "fused exchange+tables kernel over NVLink peer memory (maxstyle_tables_p2p)",
+    gstep_exchange = ({"p2p": ("one-kernel forward, (mu|sig) rows exchanged over NVLink peer memory in its channel finaliser (maxstyle_fwd_p2p)"
+                               if gstep is not None and gstep.one_kernel else
+                               "fused exchange+tables kernel over NVLink peer memory (maxstyle_tables_p2p)"),
                        "nccl": "NCCL all_gather_into_tensor captured in the forward graph"}.get(gstep.exchange, "NCCL all-gather (eager module)")
                       if gstep is not None else "NCCL all-gather (eager module)")
 

@@ -32,12 +32,14 @@ class GraphedLayerStep:
             else nccl (`self.exchange` says which).
         one_kernel (with the p2p exchange): run the whole forward as the one-kernel L2-window forward with the exchange in
             its channel finaliser (maxstyle_fwd_p2p) when the shape qualifies; False: statistics -> exchange + tables -> apply.
+            Default: on at 2 ranks, off beyond -- with more ranks the skew between them outgrows the 32 MB window that hides
+            the exchange and the apply items stall (profiles/r01_multi.txt).
     Attributes: `y`, `dx` (static outputs), `grads` = (d_gamma, d_beta, d_lmda) when the layer has no fused step or it
     keeps gradients, `kernels_per_step` (for launch accounting).
     """
 
     def __init__(self, layer: MaxStyle, x: torch.Tensor, dy: torch.Tensor, need_dx: bool = True, exchange: str = "auto",
-                 one_kernel: bool = True):
+                 one_kernel: Optional[bool] = None):
         if not x.is_cuda:
             raise RuntimeError("maxstyle_b200: GraphedLayerStep needs CUDA tensors (there is no CPU path)")
         if not layer.is_active():
@@ -64,6 +66,8 @@ class GraphedLayerStep:
             self.grads = (torch.empty(n, c, device=dev), torch.empty(n, c, device=dev), torch.empty(n, device=dev))
         self.exchange = None
         self.peer = None
+        if one_kernel is None:                                   # measured: 268 vs 275.5 us/step at 2 ranks, 307 vs 277 at 4
+            one_kernel = self.distributed and layer._exchange.world <= 2
         self.one_kernel = None if one_kernel else False          # None: ask maxstyle_fwd_p2p on the first call
         if self.distributed:
             self.table = layer._exchange.allocate(n, c, dev)
