@@ -73,8 +73,8 @@ struct FusedItem {
     int c, n, k;     // channel, sample, piece within the plane
 };
 
-// Ordered queue position -> item (see the file comment).
-__device__ __forceinline__ FusedItem fused_item(const FusedArgs& a, int64_t id) {
+// Ordered queue position -> item (see the file comment).  Host-callable: tests/host/queue_check.cu walks the whole queue.
+MS_HD FusedItem fused_item(const FusedArgs& a, int64_t id) {
     const int64_t Ic = a.items_per_channel;
     const int64_t head = (int64_t)a.window * Ic;
     FusedItem it;
