@@ -154,6 +154,12 @@ int maxstyle_tables_p2p(const uint64_t* peers, int rank, int world, uint32_t* ep
                         const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
                         float* gamma_std, float* beta_std, int flags, float* scale, float* shift, maxstyle_stream_t stream);
 
+/* Rank barrier over the exchange buffers (one warp per rank, tagged words pushed to every peer): enqueue it right before
+ * maxstyle_fwd_p2p so that all ranks start that kernel together -- the launch skew between ranks is then waited out before
+ * any streaming instead of inside the forward's L2 window.  `bar_epoch` is a device counter of its own (starts at 0). */
+int maxstyle_rank_barrier(const uint64_t* peers, int rank, int world, int N, int C, uint32_t* bar_epoch, int* error,
+                          maxstyle_stream_t stream);
+
 /* Multi-GPU whole forward in ONE kernel: the L2-window forward of maxstyle_fwd whose channel finaliser exchanges the channel's
  * (mu | sig) rows with the other ranks through the same peer-memory inboxes and epoch counter as maxstyle_tables_p2p (the
  * two calls may be mixed on one set of buffers as long as every rank makes the same sequence of calls).  x is read from HBM

@@ -51,6 +51,7 @@ SIGNATURES = {
     "maxstyle_p2p_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "maxstyle_tables_p2p": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       _vp, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, _f32p, _f32p, _vp]),
+    "maxstyle_rank_barrier": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "maxstyle_fwd_p2p": (C.c_int, [_vp, _vp, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                    _vp, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp]),

@@ -454,7 +454,19 @@ int maxstyle_tables(const float* mu_all, const float* sig_all, int table_ld, int
 
 size_t maxstyle_p2p_bytes(int N, int C, int world) {
     if (N <= 0 || C <= 0 || world <= 0) return 0;
-    return (size_t)2 * N * world * 2 * C * 8;            // two parities of {value, epoch} words for every (row, mu|sig, channel)
+    // two parities of {value, epoch} words for every (row, mu|sig, channel), then two parities of `world` barrier words
+    return ((size_t)2 * N * world * 2 * C + (size_t)2 * world) * 8;
+}
+
+int maxstyle_rank_barrier(const uint64_t* peers, int rank, int world, int N, int C, uint32_t* bar_epoch, int* error,
+                          maxstyle_stream_t stream) {
+    if (!peers || !bar_epoch || !error || world < 1 || world > 32 || rank < 0 || rank >= world || N <= 0 || C <= 0)
+        return MAXSTYLE_ERR_BAD_ARG;
+    PeerTables pt;
+    pt.peers = reinterpret_cast<const unsigned long long*>(peers);
+    pt.rank = rank; pt.world = world; pt.epoch = nullptr; pt.done = nullptr; pt.error = error;
+    rank_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pt, (size_t)2 * N * world * 2 * C, bar_epoch);
+    return check_launch();
 }
 
 int maxstyle_tables_p2p(const uint64_t* peers, int rank, int world, uint32_t* epoch, uint32_t* done, int* error,

@@ -164,6 +164,30 @@ tables_p2p_kernel(PeerTables pt, float* __restrict__ mu_all, float* __restrict__
     }
 }
 
+// Rank barrier over the same peer buffers (one warp): every rank pushes an epoch-tagged word to every peer and spins on its own
+// slots.  Launched right before the one-kernel multi-GPU forward so that the ranks START it within a microsecond or two of
+// each other: the launch skew between ranks (they replay their graphs independently) is then spent idle here, before any
+// streaming, instead of inside the forward where a channel finaliser waiting for a late rank lets x fall out of the L2 window.
+// The barrier words live behind the inboxes: [2 parities][world] x {rank, epoch}.
+__global__ void __launch_bounds__(32)
+rank_barrier_kernel(PeerTables pt, size_t barrier_offset_words, unsigned int* bar_epoch) {
+    const int t = threadIdx.x;
+    const unsigned int epoch = *(volatile unsigned int*)bar_epoch + 1u;
+    const int p = (int)(epoch & 1u);
+    if (t < pt.world && t != pt.rank) {
+        uint2* dst = reinterpret_cast<uint2*>(pt.peers[t]) + barrier_offset_words + (size_t)p * pt.world + pt.rank;
+        st_ll(dst, __int_as_float(pt.rank), epoch);
+        const uint2* src = reinterpret_cast<const uint2*>(pt.peers[pt.rank]) + barrier_offset_words + (size_t)p * pt.world + t;
+        float who;
+        const long long t0 = clock64();
+        while (!ld_ll(src, epoch, who)) {
+            if (clock64() - t0 > 4000000000LL) { *pt.error = 1; break; }
+        }
+    }
+    __syncwarp();
+    if (t == 0) *bar_epoch = epoch;
+}
+
 // Stand-alone optimiser step over the three parameter tensors (gradients supplied by the caller).
 __global__ void __launch_bounds__(256)
 step_kernel(const float* __restrict__ d_gamma, const float* __restrict__ d_beta, const float* __restrict__ d_lmda,

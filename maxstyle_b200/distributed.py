@@ -87,7 +87,9 @@ class PeerTableExchange:
         if len(ptrs) != self.world or ptrs[self.rank] != self.buffer.data_ptr():
             raise RuntimeError("maxstyle_b200: symmetric-memory rendezvous returned unexpected peer pointers")
         self.peers_dev = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.n_local, self.channels = n_local, c
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.bar_epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self.done = torch.zeros(1, dtype=torch.int32, device=device)
         self.error = torch.zeros(1, dtype=torch.int32, device=device)
         torch.cuda.synchronize(device)

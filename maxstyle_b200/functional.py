@@ -211,6 +211,14 @@ def style_tables_p2p(peer, mu_all, sig_all, row_offset: int, n_local: int, perm_
     return scale, shift
 
 
+def rank_barrier(peer) -> None:
+    """maxstyle_rank_barrier: line the ranks up (stream-ordered, on the device) before the one-kernel multi-GPU forward."""
+    rc = L.get_lib().maxstyle_rank_barrier(peer.peers_dev.data_ptr(), peer.rank, peer.world, peer.n_local, peer.channels,
+                                           peer.bar_epoch.data_ptr(), peer.error.data_ptr(), _stream())
+    L.check(rc, "maxstyle_rank_barrier")
+    launches.kernels += 1
+
+
 def forward_p2p(peer, x, mu_all, sig_all, row_offset: int, perm_dev, lmda, gamma_noise, beta_noise, gamma_std, beta_std,
                 flags: int, eps: float, workspace, scale, shift, out) -> bool:
     """maxstyle_fwd_p2p: the multi-GPU forward as ONE kernel (L2-window forward whose channel finaliser exchanges the rows

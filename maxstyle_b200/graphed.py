@@ -66,6 +66,12 @@ class GraphedLayerStep:
             self.grads = (torch.empty(n, c, device=dev), torch.empty(n, c, device=dev), torch.empty(n, device=dev))
         self.exchange = None
         self.peer = None
+        import os
+        # maxstyle_rank_barrier before the one-kernel forward: measured no gain at 2 ranks (271.6 vs 268.4 us/step,
+        # profiles/r01_multi.txt) -- the forward's multi-GPU overhead is not launch skew -- so it is off unless asked for
+        self.start_barrier = os.environ.get("MAXSTYLE_START_BARRIER", "0") == "1"
+        if one_kernel is None and os.environ.get("MAXSTYLE_ONE_KERNEL") in ("0", "1"):
+            one_kernel = os.environ["MAXSTYLE_ONE_KERNEL"] == "1"      # experiments
         if one_kernel is None:                                   # measured: 268 vs 275.5 us/step at 2 ranks, 307 vs 277 at 4
             one_kernel = self.distributed and layer._exchange.world <= 2
         self.one_kernel = None if one_kernel else False          # None: ask maxstyle_fwd_p2p on the first call
@@ -128,7 +134,10 @@ class GraphedLayerStep:
         if self.distributed:
             n = self.x.shape[0]
             if self.exchange == "p2p" and self.one_kernel is not False:
-                # whole forward in one kernel, the exchange inside its channel finaliser (maxstyle_fwd_p2p)
+                # whole forward in one kernel, the exchange inside its channel finaliser (maxstyle_fwd_p2p); the ranks are
+                # lined up first so that the launch skew between them is not waited out inside the L2 window
+                if self.one_kernel and self.start_barrier:
+                    F.rank_barrier(self.peer)
                 ok = F.forward_p2p(self.peer, self.x, self.mu_all, self.sig_all, self.row_offset, self.perm, layer.lmda,
                                    layer.gamma_noise, layer.beta_noise, layer.gamma_std, layer.beta_std, flags, layer.eps, self.ws,
                                    self.scale, self.shift, self.y)
