@@ -12,6 +12,7 @@ forward of a module and cached): construction runs that first forward eagerly, t
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -66,7 +67,6 @@ class GraphedLayerStep:
             self.grads = (torch.empty(n, c, device=dev), torch.empty(n, c, device=dev), torch.empty(n, device=dev))
         self.exchange = None
         self.peer = None
-        import os
         # maxstyle_rank_barrier before the one-kernel forward: measured no gain at 2 ranks (271.6 vs 268.4 us/step,
         # profiles/r01_multi.txt) -- the forward's multi-GPU overhead is not launch skew -- so it is off unless asked for
         self.start_barrier = os.environ.get("MAXSTYLE_START_BARRIER", "0") == "1"

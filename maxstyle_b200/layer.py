@@ -148,7 +148,7 @@ class MaxStyle(nn.Module):
         super().__setattr__(name, value)
 
     @torch.no_grad()
-    def reinit_(self, storage_active: bool = True):
+    def reinit_(self):
         """In-place `reset()` for CUDA-graph replay (StyleLoopExecutor): re-draws perm / rand_p / parameters with exactly the
         generator consumption of `init_parameters()` (so a seeded run matches three fresh constructions in the reference's
         loop, model:522-527) but writes into the EXISTING tensors -- parameter, permutation, batch-std and optimiser-state

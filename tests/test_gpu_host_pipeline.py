@@ -1,6 +1,5 @@
 """HostStepPipeline (the host-buffer entry point bench.py's e2e line times): results in the host slots must equal
 the device-resident module call step by step, with two steps in flight."""
-import numpy as np
 import pytest
 import torch
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Probe: does torch's symmetric memory (peer pointers over NVLink) work on this box?  Run under torchrun."""
-import os, sys, time, json
+import os, json
 import torch, torch.distributed as dist
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
