@@ -225,6 +225,20 @@ int maxstyle_bwd(const void* dy, const void* x, void* dx,
                  int N, int C, int H, int W, int dtype, int layout, int sweep,
                  void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
 
+/* Pixel-wise cross entropy on NCHW logits with an int64 label map [N,H,W] -- the loss whose gradient enters the inner
+ * style-optimisation loop (replaces cross_entropy_2D, src/models/custom_loss.py:1043-1105, label-map branch :1069-1078):
+ *   loss = -(1/D) sum_p mask[p] * weight[t_p] * log_softmax(logits[:, :, p])[t_p],  D = N*H*W if size_average else 1.
+ * `weight` ([C], already normalised by the caller as the reference does: w / sum(w) * C) and `mask` ([N*H*W]) may be NULL.
+ * Labels equal to -100 are ignored (F.nll_loss's default ignore_index, inherited by the reference).  One kernel each way;
+ * the forward's sum is deterministic.  `workspace`: maxstyle_ce2d_workspace_bytes() bytes, 256-byte aligned, zero-filled once.
+ * The backward takes the upstream gradient of the scalar loss from device memory (`dloss`, 1 float). */
+size_t maxstyle_ce2d_workspace_bytes(int N, int C, int H, int W);
+int maxstyle_ce2d_fwd(const void* logits, const int64_t* target, const float* weight, const float* mask, float* loss,
+                      int N, int C, int H, int W, int dtype, int size_average, void* workspace, size_t workspace_bytes,
+                      maxstyle_stream_t stream);
+int maxstyle_ce2d_bwd(const void* logits, const int64_t* target, const float* weight, const float* mask, const float* dloss,
+                      void* dlogits, int N, int C, int H, int W, int dtype, int size_average, maxstyle_stream_t stream);
+
 /* Stand-alone optimiser step on the three parameter tensors (same arithmetic as the fused
  * epilogue; used when the gradients arrive through autograd's .grad instead). */
 int maxstyle_step(const float* d_gamma, const float* d_beta, const float* d_lmda,

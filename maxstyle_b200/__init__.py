@@ -7,7 +7,8 @@ from .distributed import GlobalBatchMaxStyle, StyleTableExchange, PeerTableExcha
 from .host_pipeline import HostStepPipeline, HostStepResult
 from .executor import StyleLoopExecutor
 from .graphed import GraphedLayerStep
+from .losses import cross_entropy_2D
 
 __all__ = ["MaxStyle", "MixStyle", "FusedStyleOptimizer", "GlobalBatchMaxStyle", "StyleTableExchange", "PeerTableExchange",
-           "HostStepPipeline", "HostStepResult", "StyleLoopExecutor", "GraphedLayerStep"]
+           "HostStepPipeline", "HostStepResult", "StyleLoopExecutor", "GraphedLayerStep", "cross_entropy_2D"]
 __version__ = "0.1.0"

@@ -5,6 +5,7 @@
 #include "fused_fwd.cuh"
 #include "resident_fwd.cuh"
 #include "ring_fwd.cuh"
+#include "ce2d.cuh"
 #include "kernels_nhwc.cuh"
 
 #include <cuda_runtime.h>
@@ -574,6 +575,63 @@ int maxstyle_fwd_p2p(const void* x, void* y, float* mu_all, float* sig_all, int 
               static_cast<char*>(workspace), static_cast<cudaStream_t>(stream), N_global, row_offset, table_ld, pt};
     rc = try_fused_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW) != 0, (stats_sweep & MAXSTYLE_SWEEP_X_KEEP) != 0);
     return rc >= 0 ? rc : MAXSTYLE_ERR_UNSUPPORTED;
+}
+
+// ---- pixel-wise cross entropy ---------------------------------------------------------------
+static int ce2d_grid(int64_t P, int sms) {
+    const int64_t want = (P + kCeThreads - 1) / kCeThreads, cap = (int64_t)sms * 8;
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+size_t maxstyle_ce2d_workspace_bytes(int N, int C, int H, int W) {
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    return 256 + (size_t)148 * 8 * 2 * sizeof(float);          // counter + per-CTA partials (grid <= 8 CTAs per SM)
+}
+
+int maxstyle_ce2d_fwd(const void* logits, const int64_t* target, const float* weight, const float* mask, float* loss,
+                      int N, int C, int H, int W, int dtype, int size_average, void* workspace, size_t workspace_bytes,
+                      maxstyle_stream_t stream) {
+    if (!logits || !target || !loss || N <= 0 || C <= 0 || H <= 0 || W <= 0) return MAXSTYLE_ERR_BAD_ARG;
+    if (dtype != MAXSTYLE_F32 && dtype != MAXSTYLE_BF16) return MAXSTYLE_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < maxstyle_ce2d_workspace_bytes(N, C, H, W) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+        return MAXSTYLE_ERR_WORKSPACE;
+    const int sms = sm_count();
+    if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+    const int64_t hw = (int64_t)H * W, P = (int64_t)N * hw;
+    int grid = ce2d_grid(P, sms);
+    if (grid > 148 * 8 * 2) grid = 148 * 8 * 2;
+    const float inv = size_average ? 1.0f / (float)P : 1.0f;
+    unsigned int* counter = static_cast<unsigned int*>(workspace);
+    float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == MAXSTYLE_F32)
+        ce2d_fwd_kernel<float><<<grid, kCeThreads, 0, s>>>(static_cast<const float*>(logits), reinterpret_cast<const long long*>(target),
+                                                           weight, mask, loss, partials, counter, P, hw, C, inv);
+    else
+        ce2d_fwd_kernel<__nv_bfloat16><<<grid, kCeThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(logits),
+                                                                   reinterpret_cast<const long long*>(target), weight, mask, loss,
+                                                                   partials, counter, P, hw, C, inv);
+    return check_launch();
+}
+
+int maxstyle_ce2d_bwd(const void* logits, const int64_t* target, const float* weight, const float* mask, const float* dloss,
+                      void* dlogits, int N, int C, int H, int W, int dtype, int size_average, maxstyle_stream_t stream) {
+    if (!logits || !target || !dloss || !dlogits || N <= 0 || C <= 0 || H <= 0 || W <= 0) return MAXSTYLE_ERR_BAD_ARG;
+    if (dtype != MAXSTYLE_F32 && dtype != MAXSTYLE_BF16) return MAXSTYLE_ERR_UNSUPPORTED;
+    const int sms = sm_count();
+    if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+    const int64_t hw = (int64_t)H * W, P = (int64_t)N * hw;
+    const int grid = ce2d_grid(P, sms);
+    const float inv = size_average ? 1.0f / (float)P : 1.0f;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == MAXSTYLE_F32)
+        ce2d_bwd_kernel<float><<<grid, kCeThreads, 0, s>>>(static_cast<const float*>(logits), reinterpret_cast<const long long*>(target),
+                                                           weight, mask, dloss, static_cast<float*>(dlogits), P, hw, C, inv);
+    else
+        ce2d_bwd_kernel<__nv_bfloat16><<<grid, kCeThreads, 0, s>>>(static_cast<const __nv_bfloat16*>(logits),
+                                                                   reinterpret_cast<const long long*>(target), weight, mask, dloss,
+                                                                   static_cast<__nv_bfloat16*>(dlogits), P, hw, C, inv);
+    return check_launch();
 }
 
 int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int stats_sweep) {

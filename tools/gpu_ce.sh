@@ -1,0 +1,36 @@
+#!/bin/bash
+set -u
+OUT=gpurun_out/${1:-ce}
+mkdir -p $OUT
+timeout 300 python -m pytest tests/test_ce2d.py -m gpu -q --tb=short 2>&1 | tail -15 | tee $OUT/pytest_ce.txt
+timeout 120 python - <<'PY' 2>&1 | tail -3 | tee $OUT/ce_timing.txt
+import json, torch, torch.nn.functional as TF, sys
+sys.path.insert(0, '.')
+from maxstyle_b200.losses import cross_entropy_2D
+sys.path.insert(0, '/nonexistent')
+def ref_chain(x, t):      # the reference's op chain (custom_loss.py:1058-1078) on the GPU
+    n, c, h, w = x.shape
+    lp = TF.log_softmax(x, dim=1).transpose(1, 2).transpose(2, 3).contiguous().view(-1, c)
+    mask = torch.ones(n, 1, h, w, device=x.device).reshape(n * h * w, 1)
+    lv = TF.nll_loss(lp, t.view(-1), reduction="none") * mask.flatten()
+    return torch.sum(lv) / float(mask.numel())
+def timed(fn, it=50):
+    for _ in range(5): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(it): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / it * 1e3
+x = (torch.randn(20, 4, 224, 224, device="cuda") * 2).requires_grad_(True)
+t = torch.randint(0, 4, (20, 224, 224), device="cuda")
+def run(f):
+    def g():
+        x.grad = None
+        f(x, t).backward()
+    return g
+print(json.dumps({"shape": [20, 4, 224, 224], "fwd_bwd_us_reference_chain": round(timed(run(ref_chain)), 1),
+                  "fwd_bwd_us_torch_cross_entropy": round(timed(run(TF.cross_entropy)), 1),
+                  "fwd_bwd_us_maxstyle_b200": round(timed(run(cross_entropy_2D)), 1)}))
+PY
+timeout 400 python -m pytest tests -m gpu -q --maxfail=10 2>&1 | tail -3 | tee $OUT/pytest_gpu.txt
