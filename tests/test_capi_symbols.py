@@ -63,6 +63,24 @@ def test_bad_arguments_return_codes_not_crashes(lib):
     assert lib.maxstyle_stats(None, None, None, 4, 0, 4, 4, 1, 1, 0, 0, 1e-6, 0, None, 0, None) == 1   # M < 2
 
 
+def test_new_entry_points_validate_before_launching(lib):
+    """Peer-memory exchange, one-kernel multi-GPU forward, rank barrier and cross entropy: sizes and argument checks
+    (everything here returns before any CUDA call, so it runs on the CPU box)."""
+    # exchange buffer: two parities of 8-byte {value, epoch} words per (global row, mu|sig, channel) + two parities of barrier words
+    assert lib.maxstyle_p2p_bytes(20, 64, 2) == (2 * 40 * 2 * 64 + 2 * 2) * 8
+    assert lib.maxstyle_p2p_bytes(20, 64, 8) == (2 * 160 * 2 * 64 + 2 * 8) * 8
+    assert lib.maxstyle_p2p_bytes(0, 64, 2) == 0 and lib.maxstyle_p2p_bytes(20, 64, 0) == 0
+    assert lib.maxstyle_tables_p2p(None, 0, 2, None, None, None, None, None, 4, 8, 0, 4, 4, None, None, None, None, None, None, 0,
+                                   None, None, None) == 1
+    assert lib.maxstyle_rank_barrier(None, 0, 2, 4, 4, None, None, None) == 1
+    assert lib.maxstyle_fwd_p2p(None, None, None, None, 4, 8, 0, None, None, None, None, None, None, None, None, 4, 4, 8, 8, 0, 0, 1,
+                                1e-6, 0, None, 0, 2, None, None, 0, None) == 1
+    assert lib.maxstyle_ce2d_workspace_bytes(20, 4, 224, 224) >= 256 + 148 * 8 * 4
+    assert lib.maxstyle_ce2d_workspace_bytes(0, 4, 224, 224) == 0
+    assert lib.maxstyle_ce2d_fwd(None, None, None, None, None, 2, 3, 4, 4, 0, 1, None, 0, None) == 1
+    assert lib.maxstyle_ce2d_bwd(None, None, None, None, None, None, 2, 3, 4, 4, 0, 1, None) == 1
+
+
 def test_step_struct_layout_matches_header():
     from maxstyle_b200._lib import StepStruct
     # 2 int32 + 4 double + 4 int32 + 10 pointers
