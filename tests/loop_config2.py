@@ -136,7 +136,7 @@ def make_layers(kind, dec, cz, batch, idx, seed):
     return nn.ModuleDict({k: PortLayer(m.perm, m.gamma_noise, m.beta_noise, m.lmda) for k, m in ours.items()})
 
 
-def inner_loop(kind, enc, dec, seg, image, label, idx, n_iter, lr, seed, fused=True, timers=None):
+def inner_loop(kind, enc, dec, seg, image, label, idx, n_iter, lr, seed, fused=True, timers=None, ce=TF.cross_entropy):
     """generate_max_style_image (model:458-571): n_iter+1 decoder passes, n_iter encoder+segmentation passes with
     loss = -CE, backward into the style parameters only, Adam(lr) step."""
     code = enc(image).detach()
@@ -152,7 +152,7 @@ def inner_loop(kind, enc, dec, seg, image, label, idx, n_iter, lr, seed, fused=T
         if i > 0:
             opt.zero_grad()
             p = seg(enc(recon))
-            loss = -TF.cross_entropy(p, label)
+            loss = -ce(p, label)
             loss.backward()
             opt.step()
             layers.zero_grad()
@@ -202,23 +202,36 @@ def main():
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--n-iter", type=int, default=5)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--our-ce", action="store_true", help="replacement arms also use maxstyle_b200.cross_entropy_2D (SURVEY 8f-4) "
+                    "instead of torch's fused F.cross_entropy; the reference arm then uses the reference's op chain for the loss")
     args = ap.parse_args()
     idx = [3, 4, 5]
     enc, dec, seg, image, label = build(args.width, args.size, args.batch)
     out = {"config": f"BASELINE config 2 stand-in: width {args.width}, batch {args.batch}, {args.size}x{args.size}, layers {idx}, n_iter {args.n_iter}",
            "style_layer_shapes": [[args.batch, dec.channel_num(8 * args.width)[i], args.size // 2 ** max(0, 4 - i), args.size // 2 ** max(0, 4 - i)] for i in idx]}
+    ce_ours, ce_ref = TF.cross_entropy, TF.cross_entropy
+    if args.our_ce:
+        from maxstyle_b200 import cross_entropy_2D as ce_ours
+
+        def ce_ref(x, t):                      # custom_loss.py:1058-1078 as eager ops
+            n, c, h, w = x.shape
+            lp = TF.log_softmax(x, dim=1).transpose(1, 2).transpose(2, 3).contiguous().view(-1, c)
+            mask = torch.ones(n, 1, h, w, device=x.device).reshape(n * h * w, 1)
+            return torch.sum(TF.nll_loss(lp, t.view(-1), reduction="none") * mask.flatten()) / float(mask.numel())
+        out["loss"] = "reference op chain (port arm) vs maxstyle_b200.cross_entropy_2D (replacement arms)"
     rec = {}
     for kind in ("port", "ours"):
-        r, layers = inner_loop(kind, enc, dec, seg, image, label, idx, args.n_iter, 0.1, seed=7)
+        ce = ce_ref if kind == "port" else ce_ours
+        r, layers = inner_loop(kind, enc, dec, seg, image, label, idx, args.n_iter, 0.1, seed=7, ce=ce)
         rec[kind] = (r, {k: [p.detach().clone() for p in (m.gamma_noise, m.beta_noise, m.lmda)] for k, m in layers.items()})
-        out[f"loop_ms_{kind}"] = round(timed(lambda: inner_loop(kind, enc, dec, seg, image, label, idx, args.n_iter, 0.1, seed=7), args.reps), 2)
+        out[f"loop_ms_{kind}"] = round(timed(lambda: inner_loop(kind, enc, dec, seg, image, label, idx, args.n_iter, 0.1, seed=7, ce=ce), args.reps), 2)
         out[f"layers_only_ms_{kind}"] = round(layer_only_ms(kind, dec, 8 * args.width, args.batch, args.size, idx, args.n_iter, args.reps, seed=7), 2)
     # the same loop through the CUDA-graphed executor (maxstyle_b200.StyleLoopExecutor)
     from maxstyle_b200 import StyleLoopExecutor
     code = enc(image).detach()
     chans = dec.channel_num(code.shape[1])
     ex = StyleLoopExecutor(lambda cd, layers: dec.apply_max_style(cd, layers, idx),
-                           lambda img, lab: -TF.cross_entropy(seg(enc(img)), lab),
+                           lambda img, lab: -ce_ours(seg(enc(img)), lab),
                            args.batch, {i: chans[i] for i in idx}, n_iter=args.n_iter, lr=0.1, p=1.0)
 
     def graphed():
@@ -233,8 +246,8 @@ def main():
     out["recon_rel_diff"] = float((a - b).abs().max() / b.abs().max())
     out["note"] = ("recon after n_iter Adam steps differs where a gradient component is rounding noise (Adam turns it into a "
                    "+-lr step either way); first-pass output and first-iteration gradients are compared in tests/test_gpu_loop.py")
-    r0a, _ = inner_loop("ours", enc, dec, seg, image, label, idx, 0, 0.1, seed=7)
-    r0b, _ = inner_loop("port", enc, dec, seg, image, label, idx, 0, 0.1, seed=7)
+    r0a, _ = inner_loop("ours", enc, dec, seg, image, label, idx, 0, 0.1, seed=7, ce=ce_ours)
+    r0b, _ = inner_loop("port", enc, dec, seg, image, label, idx, 0, 0.1, seed=7, ce=ce_ref)
     out["first_pass_rel_diff"] = float((r0a - r0b).abs().max() / r0b.abs().max())
     out["loop_speedup"] = round(out["loop_ms_port"] / out["loop_ms_ours"], 3)
     out["layers_speedup"] = round(out["layers_only_ms_port"] / out["layers_only_ms_ours"], 2)
