@@ -174,3 +174,35 @@ def test_torch_port_matches_goldens(golden, manifest):
         if g[pre + "d_lmda"].size and kw.get("mix_learnable", True):
             _close(port.lmda.grad.numpy().reshape(-1), g[pre + "d_lmda"].reshape(-1), 1e-5, "port d_lmda",
                    scale=max(np.abs(g[pre + "d_lmda"]).max(), 1e-3))
+
+
+@pytest.mark.parametrize("idx", range(len(FWD_BWD_CASES)))
+def test_c_oracle_matches_reference_and_numpy_oracle(golden, manifest, idx):
+    """The C restatement (oracle/maxstyle_oracle.c, double precision, scalar loops) against the reference-generated goldens
+    and against the numpy oracle: two independently written checkers must agree to float64 rounding."""
+    from oracle import build_c as CO
+    g = golden["fwd_bwd"]
+    meta = manifest["fwd_bwd"][idx]
+    pre = f"f{idx}_"
+    shape = (meta["N"], meta["C"], meta["H"], meta["W"])
+    x = make_input(meta["seed"], shape, meta["kind"])
+    dy = np.random.RandomState(meta["seed"] + 5000).standard_normal(size=shape).astype(np.float32)
+    st = _state(g, pre, meta["kwargs"])
+    if O.is_identity_case(st, shape):
+        pytest.skip("identity case: the layer returns x itself")
+    flags = CO.flags_of(mix_style=st.mix_style, no_noise=st.no_noise, compute_std=True)
+    y, cache = CO.forward(x, st.perm, st.lmda, st.gamma_noise, st.beta_noise, eps=st.eps, flags=flags)
+    dx, dgam, dbet, dlm = CO.backward(dy, x, cache)
+    # against the numpy oracle in float64: same algorithm, different code
+    st2 = _state(g, pre, meta["kwargs"])
+    y64, c64 = O.forward(x, st2, dtype=np.float64)
+    dx64, dg64, db64, dl64 = O.backward(dy, x, st2, c64, dtype=np.float64)
+    for name, a, b in (("y", y, y64), ("mu", cache["mu"], c64.mu), ("sig", cache["sig"], c64.sig), ("dx", dx, dx64),
+                       ("d_gamma", dgam, dg64), ("d_beta", dbet, db64), ("d_lmda", dlm, dl64),
+                       ("gamma_std", cache["gamma_std"], c64.gamma_std), ("beta_std", cache["beta_std"], c64.beta_std)):
+        _close(a, b, 1e-9, f"C vs numpy oracle: {name}", scale=max(np.abs(b).max(), 1e-6))
+    # against the reference's own fp32 outputs
+    off = meta["kind"] == "offset"
+    _close(y, g[pre + "y"], 2e-4 if off else 1e-5, "y")
+    _close(dx, g[pre + "dx"], 5e-3 if off else 1e-4, "dx")
+    _close(cache["sig"], g[pre + "sig"], 2e-5 if off else 1e-5, "sig")
