@@ -140,7 +140,7 @@ def run_reference(args):
     torch.set_num_threads(threads)
     s = SHAPE
     # each "step" is the full per-GPU batch of the workload; bounded: warmup W (<=2), K steps capped by a time budget
-    budget = 60.0
+    budget = float(os.environ.get("BENCH_REF_BUDGET_S", "60"))          # tests shorten it
     res = time_cpu_baseline(s["N"], s["C"], s["H"], s["W"], budget_s=budget, min_iters=max(1, min(args.steps, 5)),
                             warmup=max(1, min(args.warmup, 2)), threads=threads)
     value = res["samples_per_s"]
