@@ -90,6 +90,7 @@ def main():
     # exchange + tables kernel (maxstyle_tables_p2p) and NCCL's all-gather captured in the graph.  Several replays walk
     # the exchange's epoch / parity scheme; every one must reproduce the golden slab.
     from maxstyle_b200 import GraphedLayerStep
+    from maxstyle_b200 import functional as F_
     layer._fused_step = None                                   # gradients only: the state stays fixed across replays
     with torch.no_grad():                                      # the fused Adam step above moved all three
         layer.gamma_noise.copy_(torch.from_numpy(g[pre + "gamma_noise"][off:off + n_loc]).view(n_loc, c, 1, 1))
@@ -120,7 +121,6 @@ def main():
         if transport.startswith("p2p"):
             gs.peer.check()
             assert int(gs.peer.epoch.item()) == 7, int(gs.peer.epoch.item())     # first forward + warm-up + 5 replays
-            from maxstyle_b200 import functional as F_
             F_.workspace_status(gs.ws, n_loc, c, h, w, 0)                        # no device-side wait timed out
         errs[f"graph_{transport}_kernels"] = float(gs.kernels_per_step)
         gs.close()
