@@ -130,34 +130,159 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation of the path (oracle port) on the host cores
 # --------------------------------------------------------------------------------------------
+def cpu_reference_timing(n, c, h, w, steps, warmup, threads, budget_s=None):
+    """The reference's CPU implementation of the path on the host cores: the UNMODIFIED reference layer from oracle/_ref
+    (kind "reference") when it has been staged, else the validated port of its op chain (kind "port")."""
+    try:
+        from oracle import ref_shims
+        if ref_shims.reference_root() is not None:
+            from oracle.ref_layer_bench import time_reference_layer
+            res = time_reference_layer(n, c, h, w, steps=steps, warmup=warmup, threads=threads, budget_s=budget_s)
+            res["what"] = ("unmodified reference MaxStyle(use_gpu=False) (src/advanced/maxstyle.py, staged in oracle/_ref): "
+                           "zero_grad, forward, backward, torch.optim.Adam(lr=0.1).step()")
+            return res
+    except Exception as e:           # noqa: BLE001  (fall back to the port, and say so)
+        print(f"[bench] reference layer unavailable ({e!r}); timing the port", file=sys.stderr)
+    from oracle.torch_port import time_cpu_baseline
+    res = time_cpu_baseline(n, c, h, w, budget_s=budget_s or 60.0, min_iters=steps, warmup=warmup, threads=threads)
+    res["kind"] = "port"
+    res["what"] = "port of the reference's ATen op chain + autograd + torch.optim.Adam (oracle/torch_port.py)"
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import torch
-    from oracle.torch_port import time_cpu_baseline
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     s = SHAPE
-    # each "step" is the full per-GPU batch of the workload; bounded: warmup W (<=2), K steps capped by a time budget
-    budget = float(os.environ.get("BENCH_REF_BUDGET_S", "60"))          # tests shorten it
-    res = time_cpu_baseline(s["N"], s["C"], s["H"], s["W"], budget_s=budget, min_iters=max(1, min(args.steps, 5)),
-                            warmup=max(1, min(args.warmup, 2)), threads=threads)
+    # a "step" is the full per-GPU batch of the workload; exactly --steps timed steps after --warmup untimed ones, unless the
+    # time budget (a few minutes at most) runs out first -- `steps` in the line says how many were timed
+    budget = float(os.environ.get("BENCH_REF_BUDGET_S", "150"))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    res = cpu_reference_timing(s["N"], s["C"], s["H"], s["W"], steps, warmup, threads, budget_s=budget)
     value = res["samples_per_s"]
-    sample = (f"{res['iters']} timed steps (best-of) of the full per-GPU batch {s['N']}x{s['C']}x{s['H']}x{s['W']} fp32, "
-              f"fwd+bwd+torch.optim.Adam step, after {max(1, min(args.warmup, 2))} warm-up")
+    sample = (f"{res['iters']} timed steps (mean) of the full per-GPU batch {s['N']}x{s['C']}x{s['H']}x{s['W']} fp32 after {warmup} warm-up: "
+              + res["what"])
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": res["iters"],
-        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": res["seconds_per_step"] * 1e3, "higher_is_better": True,
+        "warmup": warmup, "ms_per_step": res["seconds_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["threads"], "kind": res["kind"], "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference's eager ATen op chain + autograd + Adam (oracle/torch_port.py, validated against "
-                "reference-generated goldens) on the host cores; the Python reference itself cannot travel to this box",
+        "note": "the reference's own CPU implementation of the path on the box's host cores, one process (rank 0), all threads",
     }
     print(json.dumps(line))
     return 0
+
+
+# --------------------------------------------------------------------------------------------
+# untimed checks that ride along with the benchmark
+# --------------------------------------------------------------------------------------------
+def parity_check(layer, gstep, world, rank, dev, seed):
+    """This rank's outputs on the benchmarked buffers against the float64 oracle (oracle/maxstyle_oracle.py, pinned to the
+    reference by tests/test_oracle_golden.py), run AFTER the timed region: y through the very forward graph that was timed,
+    dX and the parameter gradients through the same backward kernel (without the fused step, so that the parameters stay the
+    ones the oracle is given).  Multi GPU: the oracle is the reference semantics on the CONCATENATED batch
+    (maxstyle.py:157-185 with perm over the global batch): every rank takes the float64 statistics of its own rows, the tables
+    are all-gathered (test plumbing, not the product path) and each rank checks its slice.  Errors are max-norm relative
+    (max|a-b| / max|b|), maximum over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from maxstyle_b200 import functional as F
+    from oracle import maxstyle_oracle as O
+    n, c, h, w = gstep.x.shape
+    f64 = np.float64
+    gam = layer.gamma_noise.detach().float().cpu().numpy().reshape(n, c).astype(f64)
+    bet = layer.beta_noise.detach().float().cpu().numpy().reshape(n, c).astype(f64)
+    lm = layer.lmda.detach().float().cpu().numpy().reshape(n).astype(f64)
+    gs = layer.gamma_std.detach().float().cpu().numpy().reshape(c).astype(f64)
+    bs = layer.beta_std.detach().float().cpu().numpy().reshape(c).astype(f64)
+    y = gstep.forward().clone()
+    dx, dg, db, dl = F.backward_raw(gstep.dy, gstep.x, gstep.mu_all, gstep.sig_all, gstep.row_offset, gstep.scale, gstep.perm,
+                                    layer.lmda, layer.gamma_std, layer.beta_std, gstep.flags, gstep.ws, need_dx=True)
+    torch.cuda.synchronize()
+    F.workspace_status(gstep.ws, n, c, h, w, F.dtype_code(gstep.x), F.layout_of(gstep.x))     # raises if a device-side wait gave up
+    if getattr(gstep, "peer", None) is not None:
+        gstep.peer.check()
+    x_np, dy_np = gstep.x.cpu().numpy(), gstep.dy.cpu().numpy()
+    mu, sig = O.instance_stats(x_np, layer.eps, f64)
+    row_offset = gstep.row_offset
+    if world > 1:
+        mine = torch.from_numpy(np.concatenate([mu, sig], axis=1)).to(dev)
+        table = torch.empty(world * n, 2 * c, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(table, mine)
+        table = table.cpu().numpy()
+        g_mu, g_sig = table[:, :c], table[:, c:]
+    else:
+        g_mu, g_sig = mu, sig
+    st = O.StyleState(perm=layer.perm.numpy(), gamma_noise=gam, beta_noise=bet, lmda=lm, p=1.0, gamma_std=gs, beta_std=bs)
+    y64, cache = O.forward(x_np, st, f64, global_mu=g_mu if world > 1 else None, global_sig=g_sig if world > 1 else None,
+                           row_offset=row_offset)
+    dx64, dg64, db64, dl64 = O.backward(dy_np, x_np, st, cache, f64, global_mu=g_mu if world > 1 else None,
+                                        global_sig=g_sig if world > 1 else None, row_offset=row_offset)
+
+    def rel(a, b):
+        a = a.detach().double().cpu().numpy().reshape(b.shape)
+        return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+    # the reference's draw of the permutation under this seed (maxstyle.py:55-58: CPU randperm, redrawn while it is the identity)
+    torch.manual_seed(seed)
+    ng = world * n
+    want = torch.randperm(ng)
+    while torch.equal(want, torch.arange(ng)):
+        want = torch.randperm(ng)
+    perm_exact = bool(torch.equal(want, layer.perm) and torch.equal(gstep.perm.cpu(), layer.perm.to(torch.int64)))
+    errs = {"y": rel(y, y64), "dx": rel(dx, dx64), "d_gamma": rel(dg, dg64), "d_beta": rel(db, db64), "d_lmda": rel(dl, dl64),
+            "gamma_std": float(np.abs(gs - O.batch_std(g_sig, f64)).max() / np.abs(gs).max()),
+            "beta_std": float(np.abs(bs - O.batch_std(g_mu, f64)).max() / np.abs(bs).max())}
+    t = torch.tensor(list(errs.values()) + [0.0 if perm_exact else 1.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    vals = t.tolist()
+    out = {k: vals[i] for i, k in enumerate(errs)}
+    out["perm_exact"] = vals[-1] == 0.0
+    out["ok"] = bool(out["y"] <= 1e-5 and out["perm_exact"] and all(out[k] <= 1e-4 for k in ("dx", "d_gamma", "d_beta", "d_lmda"))
+                     and out["gamma_std"] <= 1e-5 and out["beta_std"] <= 1e-5)
+    out["tolerance"] = {"y": 1e-5, "gradients": 1e-4, "norm": "max|a-b| / max|b| over the tensor, max over ranks"}
+    out["oracle"] = ("float64 numpy oracle on the concatenated global batch, computed on this box after the timed region; y from the "
+                     "timed forward graph, gradients from the timed backward kernel (fused step off)")
+    return out
+
+
+def link_ceiling(dev, world, h2d_dst, d2h_src, iters=4):
+    """Bare pinned-memory copies, one H2D and one D2H stream at once on every rank at the same time: what the host link gives
+    this rank when all N ranks copy together -- the ceiling `e2e` can reach.  GB/s each way (the slower direction)."""
+    import torch
+    import torch.distributed as dist
+    nbytes = h2d_dst.numel() * h2d_dst.element_size()
+    hin = torch.empty(h2d_dst.shape, dtype=h2d_dst.dtype, pin_memory=True)
+    hout = torch.empty(d2h_src.shape, dtype=d2h_src.dtype, pin_memory=True)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def run(k):
+        for _ in range(k):
+            with torch.cuda.stream(s1):
+                h2d_dst.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hout.copy_(d2h_src, non_blocking=True)
+        s1.synchronize(); s2.synchronize()
+
+    run(1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(iters)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return nbytes * iters / float(t.item()) / 1e9
 
 
 # --------------------------------------------------------------------------------------------
@@ -170,6 +295,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed oracle check of this rank's outputs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -283,6 +409,11 @@ def main():
     ms_per_step = total_ms / K
     value = world * n * K / (total_ms * 1e-3)
 
+    # ---- untimed: this rank's outputs against the oracle, on the path that was just timed -------------
+    parity = None
+    if not args.no_parity and gstep is not None:
+        parity = parity_check(layer, gstep, world, rank, dev, 1234)
+
     # ---- e2e: same step through the public module API from pinned host buffers --------------
     e2e = None
     if not args.no_e2e:
@@ -317,9 +448,13 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
-        e2e = {"value": world * n * ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
-               "d2h_bytes_per_step": pipe.d2h_bytes, "steps": ke, "ms_per_step": e2e_s / ke * 1e3,
-               "link_GBps_each_way": pipe.h2d_bytes / (e2e_s / ke) / 1e9,
+        del pipe, hx, hdy
+        ceiling = link_ceiling(dev, world, gstep.y if gstep is not None else torch.empty_like(dy), dy)
+        e2e = {"value": world * n * ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * E * 4,
+               "d2h_bytes_per_step": 2 * E * 4 + (2 * n * c + n) * 4, "steps": ke, "ms_per_step": e2e_s / ke * 1e3,
+               "link_GBps_each_way": 2 * E * 4 / (e2e_s / ke) / 1e9,
+               "link_ceiling_GBps_each_way": ceiling, "frac_of_link_ceiling": 2 * E * 4 / (e2e_s / ke) / 1e9 / ceiling,
+               "link_ceiling_how": "bare pinned copies, one H2D and one D2H stream at once, all ranks at the same time (257 MB each way per copy)",
                "note": "HostStepPipeline (public API): pinned host x,dy -> H2D -> layer fwd/bwd/fused step -> D2H y,dX,params "
                        "every step; 2 steps in flight so copy-in and copy-out share the full-duplex link; PCIe-bound"}
 
@@ -344,14 +479,14 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if parity is not None:
+            line["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
-            from oracle.torch_port import time_cpu_baseline
             torch.set_num_threads(os.cpu_count() or 1)
-            res = time_cpu_baseline(n, c, h, w, budget_s=12.0, min_iters=3, warmup=1, threads=os.cpu_count() or 1)
+            res = cpu_reference_timing(n, c, h, w, steps=3, warmup=1, threads=os.cpu_count() or 1, budget_s=20.0)
             line["cpu_baseline"] = {
-                "value": res["samples_per_s"], "unit": UNIT, "cores": res["threads"], "kind": "port",
-                "sample": f"{res['iters']} timed steps (best-of) of the full batch {n}x{c}x{h}x{w} fp32 fwd+bwd+Adam step "
-                          "of the reference's ATen op chain (oracle/torch_port.py), 1 warm-up",
+                "value": res["samples_per_s"], "unit": UNIT, "cores": res["threads"], "kind": res["kind"],
+                "sample": f"{res['iters']} timed steps (mean) of the full batch {n}x{c}x{h}x{w} fp32 after 1 warm-up: " + res["what"],
                 "ms_per_step": res["seconds_per_step"] * 1e3}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -82,7 +82,14 @@ enum {
                                         shape qualifies, even where the two-pass path is faster (tests)   */
     MAXSTYLE_SWEEP_FORCE_RESIDENT = 128, /* ... likewise for the shared-memory-resident kernel              */
     MAXSTYLE_SWEEP_NO_RING = 256,   /* maxstyle_fwd (stats_sweep): skip the TMA-ring version of the L2-window kernel */
-    MAXSTYLE_SWEEP_FORCE_RING = 512 /* ... take it whenever the shape qualifies                              */
+    MAXSTYLE_SWEEP_FORCE_RING = 512, /* ... take it whenever the shape qualifies                              */
+    MAXSTYLE_SWEEP_NO_CLUSTER = 1024, /* maxstyle_fwd / maxstyle_fwd_p2p (stats_sweep): skip the cluster-resident kernel */
+    MAXSTYLE_SWEEP_FORCE_CLUSTER = 2048, /* ... take it whenever the shape qualifies                           */
+    MAXSTYLE_SWEEP_CLUSTER_SIZE_SHIFT = 12,   /* bits 12-15: CTAs per cluster for the cluster-resident kernel (1, 2, 4, 8; 0 = chosen by the library) */
+    MAXSTYLE_SWEEP_CLUSTER_STAGES_SHIFT = 16, /* bits 16-18: cap on its stages per CTA (0 = as many as fit)     */
+    MAXSTYLE_SWEEP_CLUSTER_PIECES_SHIFT = 19, /* bits 19-24: pieces a plane is cut into, cluster-resident and paired kernels (0 = chosen by the library) */
+    MAXSTYLE_SWEEP_NO_PAIR = 1 << 25,         /* maxstyle_fwd / maxstyle_fwd_p2p (stats_sweep): skip the paired (piece-owning) kernel */
+    MAXSTYLE_SWEEP_FORCE_PAIR = 1 << 26       /* ... take it whenever the shape qualifies                           */
 };
 
 /* optimiser step fused into the backward epilogue (north_star item 4) */
@@ -204,6 +211,14 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig,
 /* Number of kernels maxstyle_fwd launches for this shape on the current device: 1 (resident or L2 window), 3 (two-pass:
  * stats, tables, apply), 0 for an unsupported shape.  Assumes 16-byte aligned x and y. */
 int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int stats_sweep);
+
+/* How the single-kernel forwards would run this shape on the current device in their steady state (diagnostics; no launch).
+ * With MAXSTYLE_SWEEP_FORCE_CLUSTER in stats_sweep, the cluster-resident kernel: out[0..9] = CTAs per cluster, stages per CTA,
+ * co-resident clusters, bytes of a piece per CTA, chunk bytes, chunks per part, dynamic shared memory per CTA, SMs, pieces per
+ * plane, 1 if the samples are visited in cycle order of perm.  Otherwise the paired kernel: out[2] = CTAs, out[3] = bytes per
+ * piece, out[7] = SMs, out[8] = pieces per plane, out[9] = cycle order, out[10] = 1.  `out` holds 12 ints.
+ * MAXSTYLE_ERR_UNSUPPORTED when the kernel cannot take the shape. */
+int maxstyle_fwd_geometry(int N, int C, int H, int W, int dtype, int stats_sweep, int* out);
 
 /* Debug / test helper, the only entry point that synchronises: waits for `stream` and returns
  * MAXSTYLE_ERR_TIMEOUT if a device-side wait of the fused forward gave up since the workspace

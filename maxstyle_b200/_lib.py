@@ -21,6 +21,9 @@ FLAG_MIX_STYLE, FLAG_NO_NOISE, FLAG_COMPUTE_BATCH_STD, FLAG_NO_CLAMP = 1, 2, 4, 
 STEP_NONE, STEP_ADAM, STEP_SIGN = 0, 1, 2
 SWEEP_REVERSE, SWEEP_X_KEEP, SWEEP_X_STREAM, SWEEP_IO_NORMAL, SWEEP_NO_FUSED = 1, 2, 4, 8, 16
 SWEEP_NO_RESIDENT, SWEEP_FORCE_WINDOW, SWEEP_FORCE_RESIDENT, SWEEP_NO_RING, SWEEP_FORCE_RING = 32, 64, 128, 256, 512
+SWEEP_NO_CLUSTER, SWEEP_FORCE_CLUSTER = 1024, 2048
+SWEEP_CLUSTER_SIZE_SHIFT, SWEEP_CLUSTER_STAGES_SHIFT, SWEEP_CLUSTER_PIECES_SHIFT = 12, 16, 19
+SWEEP_NO_PAIR, SWEEP_FORCE_PAIR = 1 << 25, 1 << 26
 
 _f32p = C.c_void_p      # device pointers travel as plain addresses
 _vp = C.c_void_p
@@ -61,6 +64,7 @@ SIGNATURES = {
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
     "maxstyle_fwd_kernels": (C.c_int, [C.c_int] * 7),
+    "maxstyle_fwd_geometry": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int)]),
     "maxstyle_workspace_status": (C.c_int, [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "maxstyle_bwd": (C.c_int, [_vp, _vp, _vp, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _vp, _f32p, _f32p, _f32p,
                                C.c_int, _f32p, _f32p, _f32p, C.POINTER(StepStruct),

@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmaxstyle_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["common.cuh", "plan.h", "kernels_nchw.cuh", "kernels_nhwc.cuh", "fused_fwd.cuh", "resident_fwd.cuh", "ring_fwd.cuh", "ce2d.cuh", "tables.cuh", os.path.join("..", "..", "include", "maxstyle_b200.h")]
+HEADERS = ["common.cuh", "plan.h", "kernels_nchw.cuh", "kernels_nhwc.cuh", "fused_fwd.cuh", "resident_fwd.cuh", "ring_fwd.cuh", "cluster_fwd.cuh", "pair_fwd.cuh", "ce2d.cuh", "tables.cuh", os.path.join("..", "..", "include", "maxstyle_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",     # B200 only; no PTX for other targets, no fallback arch
     "-lineinfo", "-O3", "-std=c++17",

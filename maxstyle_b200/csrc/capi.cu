@@ -5,6 +5,8 @@
 #include "fused_fwd.cuh"
 #include "resident_fwd.cuh"
 #include "ring_fwd.cuh"
+#include "cluster_fwd.cuh"
+#include "pair_fwd.cuh"
 #include "ce2d.cuh"
 #include "kernels_nhwc.cuh"
 
@@ -390,6 +392,209 @@ int try_resident_fwd(const FwdCall& f, const Workspace& w, int sms, int stats_sw
                              : launch_resident<__nv_bfloat16, 256, 4>(f, a, rp, sms);
 }
 
+// ---- cluster-resident forward -------------------------------------------------------------------------
+template <typename T>
+cudaError_t cluster_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int cs, int smem, cudaStream_t s) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kClThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaSuccess;
+}
+
+// Clusters of `cs` CTAs with `smem` bytes each that the device keeps resident at once (cached per device / type / geometry).
+template <typename T>
+int cluster_capacity(int cs, int smem) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int>, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    const auto key = std::make_tuple(dev, cs, smem);
+    std::lock_guard<std::mutex> lock(mu);
+    const auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    auto kern = fwd_cluster_kernel<T>;
+    int n = 0;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    cluster_config<T>(cfg, attr, cs, cs, smem, nullptr);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kResidentMaxSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    cache[key] = n;
+    return n;
+}
+
+struct ClusterChoice {
+    ClusterPlan plan;
+    int clusters;      // G
+    int use_order;     // visit the samples in cycle order of perm
+};
+
+// What the launch has to respect: `whole_channel` -- an item waits for planes anywhere in its channel in the order the ranks
+// agree on (first forward: batch std; multi GPU: partners on other ranks) -- needs all N*P items of a channel inside one
+// round of clusters; otherwise the samples can be visited in cycle order of perm, where an item only waits for its plane's
+// other pieces and the next plane (2P items).
+struct ClusterNeeds { int N; bool whole_channel; bool has_partner; };
+
+// Pick cluster size and pieces: every SM busy, >= 3-4 stages per CTA, few idle slots in the last round, few pieces.
+template <typename T>
+ClusterChoice choose_cluster(int64_t planes, int64_t M, int dtype, int align, int sms, int sweep, ClusterNeeds need) {
+    static const int64_t env_cs = env_or("MAXSTYLE_CLUSTER_CS", 0, 1);
+    static const int64_t env_stages = env_or("MAXSTYLE_CLUSTER_STAGES", kClusterMaxStages, 1);
+    static const int64_t env_pieces = env_or("MAXSTYLE_CLUSTER_PIECES", 0, 1);
+    const int sweep_cs = (sweep >> MAXSTYLE_SWEEP_CLUSTER_SIZE_SHIFT) & 15, sweep_stages = (sweep >> MAXSTYLE_SWEEP_CLUSTER_STAGES_SHIFT) & 7;
+    const int sweep_pieces = (sweep >> MAXSTYLE_SWEEP_CLUSTER_PIECES_SHIFT) & 63;
+    const int64_t force_cs = sweep_cs ? sweep_cs : env_cs;
+    const int64_t max_stages = sweep_stages ? sweep_stages : env_stages;
+    const int64_t force_pieces = sweep_pieces ? sweep_pieces : env_pieces;
+    static const int piece_options[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+    ClusterChoice best{};
+    double best_score = 0.0;
+    for (int cs = 1; cs <= kClMaxCluster; cs *= 2) {
+        if (force_cs > 0 && cs != force_cs) continue;
+        for (int P : piece_options) {
+            if (force_pieces > 0 && P != force_pieces) continue;
+            const ClusterPlan cp = make_cluster_plan(M, dtype, align, cs, P, (int)max_stages);
+            if (!cp.ok) continue;
+            const int64_t items = planes * P;
+            int64_t G = cluster_capacity<T>(cs, cp.smem);
+            if (G <= 0) continue;
+            if (G > items) G = items;
+            int use_order = 0;
+            if ((int64_t)need.N * P > G && (need.has_partner || need.whole_channel)) {
+                if (need.whole_channel || need.N > kClMaxN || 2 * P > G) continue;
+                use_order = 1;
+            }
+            const double sm_use = (double)(G * cs) / sms > 1.0 ? 1.0 : (double)(G * cs) / sms;
+            const double quant = (double)items / (double)(ceil_div(items, G) * G);
+            const double stage = cp.stages >= 4 ? 1.0 : (cp.stages == 3 ? 0.97 : (cp.stages == 2 ? 0.88 : 0.72));
+            const double piece = 1.0 - 0.004 * (P - 1) - (cs > 2 ? 0.02 : 0.0);
+            const double score = sm_use * quant * stage * piece;
+            if (score > best_score) { best_score = score; best.plan = cp; best.clusters = (int)G; best.use_order = use_order; }
+        }
+    }
+    return best;
+}
+
+template <typename T>
+int launch_cluster(const FwdCall& f, const Workspace& w, int sms, bool force, int sweep) {
+    const bool multi = f.pt.world > 1, first = (f.flags & MAXSTYLE_COMPUTE_BATCH_STD) != 0;
+    const bool mix = (f.flags & MAXSTYLE_MIX_STYLE) != 0;
+    if (first && f.n_global > kClusterStdRows) return -1;
+    const ClusterNeeds need{f.N, first || multi, mix};
+    const ClusterChoice ch = choose_cluster<T>((int64_t)f.N * f.C, f.M, f.dtype, common_align(f.x, f.y), sms, sweep, need);
+    if (!ch.plan.ok || ch.clusters <= 0) return -1;
+    const ClusterPlan& cp = ch.plan;
+    if (cp.pieces > cluster_max_pieces(f.M, f.dtype)) return -1;
+    static const int64_t enabled = env_or("MAXSTYLE_CLUSTER", 1, 1);
+    if (!force && enabled == 2) return -1;                    // MAXSTYLE_CLUSTER=2: only when forced
+    ClusterArgs a{};
+    a.N = f.N; a.C = f.C; a.M = f.M;
+    a.plane_bytes = cp.plane_bytes; a.pieces = cp.pieces; a.part_bytes = cp.part_bytes; a.part_stride = cp.part_stride;
+    a.chunk_bytes = cp.chunk_bytes; a.chunks = cp.chunks; a.stages = cp.stages; a.cluster = cp.cluster;
+    a.num_clusters = ch.clusters; a.use_order = ch.use_order; a.total_items = (int64_t)f.N * f.C * cp.pieces;
+    a.flags = f.flags; a.eps = f.eps;
+    a.in_policy = kPolicyStream; a.io_policy = kPolicyStream;
+    a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
+    a.n_global = f.n_global; a.row_offset = f.row_offset; a.ld = f.ld;
+    a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
+    a.gamma_std = f.gamma_std; a.beta_std = f.beta_std;
+    a.ll = reinterpret_cast<uint2*>(f.ws + w.cl_words);
+    a.piece_ll = reinterpret_cast<uint2*>(f.ws + w.cl_pieces);
+    a.epoch = multi ? f.pt.epoch : reinterpret_cast<unsigned int*>(f.ws + w.res_error + 24);
+    a.done = reinterpret_cast<unsigned int*>(f.ws + w.res_error + 16);
+    a.error = reinterpret_cast<int*>(f.ws + w.res_error);
+    a.pt = f.pt;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    cluster_config<T>(cfg, attr, ch.clusters * cp.cluster, cp.cluster, cp.smem, f.stream);
+    if (cudaLaunchKernelEx(&cfg, fwd_cluster_kernel<T>, static_cast<const T*>(f.x), static_cast<T*>(f.y), a) != cudaSuccess) {
+        cudaGetLastError();
+        return MAXSTYLE_ERR_CUDA;
+    }
+    return check_launch();
+}
+
+// Same contract as try_fused_fwd.  `preferred`: shapes where this kernel is the default.
+int try_cluster_fwd(const FwdCall& f, const Workspace& w, int sms, int sweep) {
+    const bool force = (sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER) != 0;
+    const int64_t pb = f.M * elem_size(f.dtype);
+    if (f.N < 2 || pb < kClusterMinPlaneBytes) return -1;
+    static const int64_t enabled = env_or("MAXSTYLE_CLUSTER", 1, 1);
+    if (!force && enabled == 0) return -1;
+    return f.dtype == MAXSTYLE_F32 ? launch_cluster<float>(f, w, sms, force, sweep) : launch_cluster<__nv_bfloat16>(f, w, sms, force, sweep);
+}
+
+// ---- paired forward -----------------------------------------------------------------------------------
+template <typename T, int VEC>
+void launch_pair(const FwdCall& f, const PairArgs& a, int grid) {
+    fwd_pair_kernel<T, VEC, vpt_for<VEC, 1>()><<<grid, kThreads, 0, f.stream>>>(static_cast<const T*>(f.x), static_cast<T*>(f.y), a);
+}
+
+struct PairChoice { PairPlan plan; int grid; int use_order; };
+
+PairChoice choose_pair(int N, int C, int64_t M, int dtype, int align, int sms, int sweep, bool whole_channel, bool has_partner) {
+    PairChoice ch{};
+    const int force_pieces = (sweep >> MAXSTYLE_SWEEP_CLUSTER_PIECES_SHIFT) & 63;
+    ch.plan = make_pair_plan(M, dtype, align, force_pieces);
+    if (!ch.plan.ok) return ch;
+    const int64_t items = (int64_t)N * C * ch.plan.pieces, cap = (int64_t)sms * kBlocksPerSM;
+    ch.grid = (int)(items < cap ? items : cap);
+    // an item waits for items within W positions: grid > W keeps a CTA free for the lowest missing one
+    if ((int64_t)N * ch.plan.pieces >= ch.grid && (has_partner || whole_channel)) {
+        if (whole_channel || N > kPairMaxN || 2 * ch.plan.pieces >= ch.grid) { ch.plan.ok = false; return ch; }
+        ch.use_order = 1;
+    }
+    return ch;
+}
+
+// Same contract as try_fused_fwd.
+int try_pair_fwd(const FwdCall& f, const Workspace& w, int sms, int sweep) {
+    const bool force = (sweep & MAXSTYLE_SWEEP_FORCE_PAIR) != 0;
+    static const int64_t enabled = env_or("MAXSTYLE_PAIR", 1, 1);
+    if (!force && enabled != 1) return -1;
+    if (f.N < 2) return -1;
+    const bool multi = f.pt.world > 1, first = (f.flags & MAXSTYLE_COMPUTE_BATCH_STD) != 0;
+    if (first && f.n_global > 32 * kPairStdRows) return -1;
+    const PairChoice ch = choose_pair(f.N, f.C, f.M, f.dtype, common_align(f.x, f.y), sms, sweep, first || multi, (f.flags & MAXSTYLE_MIX_STYLE) != 0);
+    if (!ch.plan.ok || ch.plan.pieces > w.max_pieces) return -1;
+    PairArgs a{};
+    a.N = f.N; a.C = f.C; a.M = f.M;
+    a.nvec = ch.plan.nvec; a.pieces = ch.plan.pieces; a.piece_vecs = ch.plan.piece_vecs; a.use_order = ch.use_order;
+    a.total_items = (int64_t)f.N * f.C * ch.plan.pieces;
+    a.flags = f.flags; a.eps = f.eps;
+    a.pol_first = (sweep & MAXSTYLE_SWEEP_X_STREAM) ? kPolicyNormal : kPolicyKeep;       // the piece is re-read microseconds later
+    a.pol_second = kPolicyStream; a.pol_out = kPolicyStream;
+    a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
+    a.n_global = f.n_global; a.row_offset = f.row_offset; a.ld = f.ld;
+    a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
+    a.gamma_std = f.gamma_std; a.beta_std = f.beta_std;
+    a.ll = reinterpret_cast<uint2*>(f.ws + w.cl_words);
+    a.piece_ll = reinterpret_cast<uint2*>(f.ws + w.cl_pieces);
+    a.epoch = multi ? f.pt.epoch : reinterpret_cast<unsigned int*>(f.ws + w.res_error + 24);
+    a.queue = reinterpret_cast<unsigned long long*>(f.ws + w.res_error + 8);
+    a.done = reinterpret_cast<unsigned int*>(f.ws + w.res_error + 16);
+    a.error = reinterpret_cast<int*>(f.ws + w.res_error);
+    a.pt = f.pt;
+    if (f.dtype == MAXSTYLE_F32) {
+        if (ch.plan.vec == 8) launch_pair<float, 8>(f, a, ch.grid); else launch_pair<float, 4>(f, a, ch.grid);
+    } else {
+        if (ch.plan.vec == 16) launch_pair<__nv_bfloat16, 16>(f, a, ch.grid); else launch_pair<__nv_bfloat16, 8>(f, a, ch.grid);
+    }
+    return check_launch();
+}
+
 }  // namespace
 
 extern "C" {
@@ -529,6 +734,16 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
         if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
         FwdCall f{x, y, mu, sig, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, M, dtype, flags, eps,
                   static_cast<char*>(workspace), static_cast<cudaStream_t>(stream), N, 0, C, PeerTables{}};
+        const int force_other = stats_sweep & (MAXSTYLE_SWEEP_FORCE_RESIDENT | MAXSTYLE_SWEEP_FORCE_RING | MAXSTYLE_SWEEP_FORCE_WINDOW);
+        const int force_any = force_other | (stats_sweep & (MAXSTYLE_SWEEP_FORCE_CLUSTER | MAXSTYLE_SWEEP_FORCE_PAIR));
+        if (!(stats_sweep & MAXSTYLE_SWEEP_NO_PAIR) && (!force_any || (stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR))) {
+            rc = try_pair_fwd(f, w, sms, stats_sweep);
+            if (rc >= 0) return rc;
+        }
+        if (!(stats_sweep & MAXSTYLE_SWEEP_NO_CLUSTER) && (stats_sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER)) {
+            rc = try_cluster_fwd(f, w, sms, stats_sweep);
+            if (rc >= 0) return rc;
+        }
         if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RESIDENT)) {
             rc = try_resident_fwd(f, w, sms, stats_sweep, apply_sweep, (stats_sweep & MAXSTYLE_SWEEP_FORCE_RESIDENT) != 0);
             if (rc >= 0) return rc;
@@ -573,6 +788,14 @@ int maxstyle_fwd_p2p(const void* x, void* y, float* mu_all, float* sig_all, int 
     pt.error = reinterpret_cast<int*>(static_cast<char*>(workspace) + w.res_error);
     FwdCall f{x, y, mu_all, sig_all, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, M, dtype, flags, eps,
               static_cast<char*>(workspace), static_cast<cudaStream_t>(stream), N_global, row_offset, table_ld, pt};
+    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_PAIR) && !(stats_sweep & (MAXSTYLE_SWEEP_FORCE_WINDOW | MAXSTYLE_SWEEP_FORCE_CLUSTER))) {
+        rc = try_pair_fwd(f, w, sms, stats_sweep);
+        if (rc >= 0) return rc;
+    }
+    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_CLUSTER) && (stats_sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER)) {
+        rc = try_cluster_fwd(f, w, sms, stats_sweep);
+        if (rc >= 0) return rc;
+    }
     rc = try_fused_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW) != 0, (stats_sweep & MAXSTYLE_SWEEP_X_KEEP) != 0);
     return rc >= 0 ? rc : MAXSTYLE_ERR_UNSUPPORTED;
 }
@@ -638,6 +861,27 @@ int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int 
     if (check_shape(N, C, H, W, dtype, layout) != MAXSTYLE_OK) return 0;
     if ((stats_sweep & MAXSTYLE_SWEEP_NO_FUSED) || is_nhwc(layout, C)) return 3;
     const int64_t M = (int64_t)H * W;
+    const int force_other = stats_sweep & (MAXSTYLE_SWEEP_FORCE_RESIDENT | MAXSTYLE_SWEEP_FORCE_RING | MAXSTYLE_SWEEP_FORCE_WINDOW);
+    const int force_any = force_other | (stats_sweep & (MAXSTYLE_SWEEP_FORCE_CLUSTER | MAXSTYLE_SWEEP_FORCE_PAIR));
+    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_PAIR) && (!force_any || (stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR)) && N >= 2) {
+        static const int64_t pair_enabled = env_or("MAXSTYLE_PAIR", 1, 1);
+        if ((stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR) || pair_enabled == 1) {
+            const PairChoice ch = choose_pair(N, C, M, dtype, 32, sm_count(), stats_sweep, false, true);
+            if (ch.plan.ok && ch.plan.pieces <= workspace_layout(N, C, M, dtype).max_pieces) return 1;
+        }
+    }
+    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_CLUSTER) && (stats_sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER) && N >= 2 &&
+        M * elem_size(dtype) >= kClusterMinPlaneBytes) {
+        // steady state (cached batch std): the first forward of a module may take another path when N exceeds the clusters
+        static const int64_t enabled = env_or("MAXSTYLE_CLUSTER", 1, 1);
+        const bool force = (stats_sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER) != 0;
+        if (force || enabled == 1) {
+            const ClusterNeeds need{N, false, true};
+            const ClusterChoice ch = dtype == MAXSTYLE_F32 ? choose_cluster<float>((int64_t)N * C, M, dtype, 32, sm_count(), stats_sweep, need)
+                                                           : choose_cluster<__nv_bfloat16>((int64_t)N * C, M, dtype, 32, sm_count(), stats_sweep, need);
+            if (ch.plan.ok && ch.clusters > 0) return 1;
+        }
+    }
     if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RESIDENT)) {
         const ResidentPlan rp = make_resident_plan(N, C, M, dtype, 32);
         if (rp.ok && (rp.preferred || (stats_sweep & MAXSTYLE_SWEEP_FORCE_RESIDENT))) {   // same grid rule as launch_resident
@@ -658,6 +902,28 @@ int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int 
     }
     const FusedPlan fp = make_fused_plan(N, C, M, dtype, 32);
     return fp.ok && (fp.profitable || (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW)) ? 1 : 3;
+}
+
+int maxstyle_fwd_geometry(int N, int C, int H, int W, int dtype, int stats_sweep, int* out) {
+    if (!out || check_shape(N, C, H, W, dtype, MAXSTYLE_NCHW) != MAXSTYLE_OK) return MAXSTYLE_ERR_BAD_ARG;
+    const int sms = sm_count();
+    if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+    const int64_t M = (int64_t)H * W;
+    for (int i = 0; i < 12; ++i) out[i] = 0;
+    if (!(stats_sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER)) {
+        const PairChoice pc = choose_pair(N, C, M, dtype, 32, sms, stats_sweep, false, true);
+        if (!pc.plan.ok) return MAXSTYLE_ERR_UNSUPPORTED;
+        out[2] = pc.grid; out[3] = pc.plan.piece_vecs * pc.plan.vec * elem_size(dtype); out[7] = sms; out[8] = pc.plan.pieces; out[9] = pc.use_order;
+        out[10] = 1;
+        return MAXSTYLE_OK;
+    }
+    const ClusterNeeds need{N, false, true};
+    const ClusterChoice ch = dtype == MAXSTYLE_F32 ? choose_cluster<float>((int64_t)N * C, M, dtype, 32, sms, stats_sweep, need)
+                                                   : choose_cluster<__nv_bfloat16>((int64_t)N * C, M, dtype, 32, sms, stats_sweep, need);
+    if (!ch.plan.ok || ch.clusters <= 0) return MAXSTYLE_ERR_UNSUPPORTED;
+    out[0] = ch.plan.cluster; out[1] = ch.plan.stages; out[2] = ch.clusters; out[3] = ch.plan.part_bytes;
+    out[4] = ch.plan.chunk_bytes; out[5] = ch.plan.chunks; out[6] = ch.plan.smem; out[7] = sms; out[8] = ch.plan.pieces; out[9] = ch.use_order;
+    return MAXSTYLE_OK;
 }
 
 int maxstyle_workspace_status(const void* workspace, size_t workspace_bytes, int N, int C, int H, int W, int dtype, int layout,

@@ -1,0 +1,379 @@
+// Paired forward: the whole MaxStyle forward (maxstyle.py:157-185) in ONE persistent kernel that reads x from HBM once
+// and keeps every SM streaming all the time.
+//
+// In the steady state of the layer (gamma_std / beta_std cached, maxstyle.py:165-168) a plane depends on exactly ONE other
+// plane: its mixing partner (perm[n], same channel).  So the unit of work is a PIECE of a plane (32-64 KB) that one CTA
+// owns for both of its uses, back to back:
+//     pass 1   stream the piece with 256-bit loads, shifted moments (the arithmetic of stats_nchw_kernel)       [HBM -> L2 -> SM]
+//     publish  the piece's (mean, M2) as two 8-byte {value, tag} words; fetch the plane's other pieces, merge them in piece
+//              order (every owner of a piece computes the same plane statistics); the owner of piece 0 publishes (mu, sig) --
+//              and pushes them into the peers' inboxes when the batch is sharded over GPUs
+//     partner  fetch (mu, sig) of the partner plane (first forward: of the whole channel, and take the batch std)
+//     pass 2   stream the SAME piece again -- it was read a few microseconds ago and is still in L2 -- and write
+//              y = (x - mu) * A/sig + B                                                                           [L2 -> SM -> HBM]
+// 4 CTAs x 256 threads per SM run this loop out of phase, so while one CTA sits in its publish/partner gap (2-3 us of L2
+// round trips) the other three stream; the pieces live in L2 only between their two passes (592 CTAs x <= 64 KB ~ 30 MB of
+// the 126 MB), so the second read never goes to HBM.  Compared with fused_fwd.cuh (ordered statistics / apply queue with a
+// 32 MB window): no control warp, no named-barrier hand-off per item, no channel-wide finaliser on the steady-state path, and
+// the re-read follows the first read by microseconds instead of by a window of 6 channels.
+// Items are taken with an atomic ticket, in order (channel-major; the pieces of a plane adjacent).  An item publishes before
+// it waits and only waits for items within W positions of it: W = N*P (whole channel: first forward / multi GPU) or 2P when
+// the samples are visited in cycle order of perm (the partner plane is then the NEXT plane).  The ticket of the next item is
+// taken only after the wait, so a CTA never parks a ticket behind a wait; with more CTAs than W some CTA is always free to
+// take the lowest missing item: no deadlock, no co-residency assumption beyond grid > W (host-side condition).
+#pragma once
+#include "common.cuh"
+#include "kernels_nchw.cuh"
+#include "tables.cuh"
+#include "fused_fwd.cuh"
+
+namespace ms {
+
+constexpr int kPairMaxN = 1024;          // rows of the order table
+constexpr int kPairStdRows = 16;         // first forward: rows of the channel a lane keeps in registers (n_global <= 512)
+constexpr long long kPairSpinLocal = 4000000000LL;      // ~2 s
+constexpr long long kPairSpinPeer = 40000000000LL;      // ~20 s: another rank may be late
+
+struct PairArgs {
+    int N, C;
+    int64_t M;
+    int nvec;                  // vectors per plane
+    int pieces;                // P
+    int piece_vecs;            // vectors per piece (the last piece of a plane may be shorter)
+    int use_order;             // samples visited in cycle order of perm
+    int64_t total_items;       // N * C * P
+    int flags;
+    float eps;
+    int pol_first, pol_second, pol_out;
+    float *mu, *sig;           // [n_global, ld]
+    float *scale, *shift;      // [N, C]
+    int n_global, row_offset, ld;
+    const int64_t* perm;
+    const float *lmda, *gamma_noise, *beta_noise;
+    float *gamma_std, *beta_std;
+    uint2* ll;                 // [n_global][2][C] {value, tag} words (single GPU: workspace; multi GPU: the own inbox is used instead)
+    uint2* piece_ll;           // [N*C][P][2]
+    unsigned int* epoch;       // launch counter the tag comes from (multi GPU: the exchange epoch)
+    unsigned long long* queue;
+    unsigned int* done;
+    int* error;
+    PeerTables pt;
+};
+
+__device__ __forceinline__ void pair_fail(int* error) {
+    *error = 1;
+    __threadfence_system();
+    __trap();
+}
+__device__ __forceinline__ void st_ll_dev(void* p, float v, unsigned int tag) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+}
+// Poll a pair of {value, tag} words until both carry `tag`.
+__device__ __forceinline__ void pair_poll(const uint2* w0, const uint2* w1, unsigned int tag, bool remote, int* error, float& v0, float& v1) {
+    if (ld_ll(w0, tag, v0) & ld_ll(w1, tag, v1)) return;
+    const long long t0 = clock64();
+    const long long limit = remote ? kPairSpinPeer : kPairSpinLocal;
+    while (!(ld_ll(w0, tag, v0) & ld_ll(w1, tag, v1))) {
+        __nanosleep(32);
+        if (clock64() - t0 > limit) pair_fail(error);
+    }
+}
+
+// Everything between the two passes of a piece, run by warp 0 (kept out of line so that its register needs -- the rows of a
+// channel on the first forward -- do not spill into the streaming loops): publish the piece, merge the plane, publish the
+// plane (piece 0), fetch the partner / the channel, style coefficients -> coef[0..2], then the ticket of the next item.
+template <int VEC>
+__device__ __noinline__ void pair_resolve(const PairArgs& a, Moments m, float K, int c, int n, int p, unsigned int tag, uint2* ll_mine,
+                                          size_t ll_words, float* coef, long long* next_id) {
+    const int lane = threadIdx.x & 31;
+    const int P = a.pieces;
+    const bool multi = a.pt.world > 1;
+    const bool mix = a.flags & 1, no_noise = a.flags & 2, compute_std = a.flags & 4;
+    const float inv_m1 = 1.0f / (float)(a.M - 1);
+    const int lo = a.row_offset, hi = a.row_offset + a.N, NG = a.n_global;
+    const int64_t plane = (int64_t)n * a.C + c;
+                const int row = lo + n;
+                const int prow = mix ? (int)a.perm[row] : row;
+                const float lm = mix ? a.lmda[n] : 0.f;
+                float gn = 0.f, bn = 0.f, gs = 0.f, bs = 0.f;
+                if (!no_noise) {
+                    gn = a.gamma_noise[plane]; bn = a.beta_noise[plane];
+                    if (!compute_std) { gs = a.gamma_std[c]; bs = a.beta_std[c]; }
+                }
+                if (P > 1) {
+                    uint2* mine = a.piece_ll + ((size_t)plane * P + p) * 2;
+                    if (lane == 0) { st_ll_dev(mine, m.mean, tag); st_ll_dev(mine + 1, m.m2, tag); }
+                    float pm = m.mean, pq = m.m2;
+                    if (lane < P && lane != p) {
+                        const uint2* w = a.piece_ll + ((size_t)plane * P + lane) * 2;
+                        pair_poll(w, w + 1, tag, false, a.error, pm, pq);
+                    }
+                    __syncwarp();
+                    Moments tot{0.f, 0.f, 0.f};
+                    for (int l = 0; l < P; ++l) {
+                        const float lmean = __shfl_sync(0xffffffffu, pm, l), lm2 = __shfl_sync(0xffffffffu, pq, l);
+                        const int cnt = (min(a.nvec, (l + 1) * a.piece_vecs) - l * a.piece_vecs) * VEC;
+                        tot = merge(tot, Moments{(float)cnt, lmean, lm2});
+                    }
+                    m = tot;
+                }
+                const float mean = K + m.mean;
+                const float sg = sqrtf(m.m2 * inv_m1 + a.eps);
+                if (p == 0) {
+                    uint2* w = ll_mine + ((size_t)row * 2) * a.C + c;
+                    if (multi) {
+                        if (lane == 0) { st_ll(w, mean, tag); st_ll(w + a.C, sg, tag); }
+                        for (int r = lane; r < a.pt.world; r += 32) {
+                            if (r == a.pt.rank) continue;
+                            uint2* dst = reinterpret_cast<uint2*>(a.pt.peers[r]) + (tag & 1u) * ll_words + ((size_t)row * 2) * a.C + c;
+                            st_ll(dst, mean, tag);
+                            st_ll(dst + a.C, sg, tag);
+                        }
+                    } else if (lane == 0) {
+                        st_ll_dev(w, mean, tag);
+                        st_ll_dev(w + a.C, sg, tag);
+                    }
+                    if (lane == 0) {
+                        a.mu[(int64_t)row * a.ld + c] = mean;
+                        a.sig[(int64_t)row * a.ld + c] = sg;
+                    }
+                }
+                if (compute_std) {
+                    // first forward (maxstyle.py:165-168): the whole channel; lane l keeps rows l, l+32, ... in registers
+                    float rm[kPairStdRows], rs[kPairStdRows];
+    #pragma unroll
+                    for (int i = 0; i < kPairStdRows; ++i) {
+                        const int r = lane + 32 * i;
+                        rm[i] = 0.f; rs[i] = 0.f;
+                        if (r < NG) {
+                            if (r == row) { rm[i] = mean; rs[i] = sg; }
+                            else {
+                                const bool remote = r < lo || r >= hi;
+                                const uint2* w = ll_mine + ((size_t)r * 2) * a.C + c;
+                                pair_poll(w, w + a.C, tag, remote, a.error, rm[i], rs[i]);
+                                if (remote && p == 0) { a.mu[(int64_t)r * a.ld + c] = rm[i]; a.sig[(int64_t)r * a.ld + c] = rs[i]; }
+                            }
+                        }
+                    }
+                    float s_sig = 0.f, s_mu = 0.f;
+    #pragma unroll
+                    for (int i = 0; i < kPairStdRows; ++i) { s_sig += rs[i]; s_mu += rm[i]; }      // rows >= NG hold zeros
+                    s_sig = warp_sum(s_sig);
+                    s_mu = warp_sum(s_mu);
+                    const float mean_sig = s_sig / (float)NG, mean_mu = s_mu / (float)NG;
+                    float q_sig = 0.f, q_mu = 0.f;
+    #pragma unroll
+                    for (int i = 0; i < kPairStdRows; ++i) {
+                        if (lane + 32 * i < NG) {
+                            const float ds = rs[i] - mean_sig, dm = rm[i] - mean_mu;
+                            q_sig = fmaf(ds, ds, q_sig);
+                            q_mu = fmaf(dm, dm, q_mu);
+                        }
+                    }
+                    q_sig = warp_sum(q_sig);
+                    q_mu = warp_sum(q_mu);
+                    gs = sqrtf(q_sig / (float)(NG - 1));
+                    bs = sqrtf(q_mu / (float)(NG - 1));
+                    if (lane == 0 && n == 0 && p == 0 && a.gamma_std != nullptr) { a.gamma_std[c] = gs; a.beta_std[c] = bs; }
+                }
+                if (lane == 0) {
+                    float mu_p = mean, sg_p = sg;
+                    if (prow != row) {
+                        const bool remote = prow < lo || prow >= hi;
+                        const uint2* w = ll_mine + ((size_t)prow * 2) * a.C + c;
+                        pair_poll(w, w + a.C, tag, remote, a.error, mu_p, sg_p);
+                        if (remote && p == 0) {                      // the backward reads the partner's row from the local table
+                            a.mu[(int64_t)prow * a.ld + c] = mu_p;
+                            a.sig[(int64_t)prow * a.ld + c] = sg_p;
+                        }
+                    }
+                    float sc, shf;
+                    style_coeffs(sg, mean, sg_p, mu_p, mix, no_noise, lm, gn, bn, gs, bs, sc, shf, !(a.flags & 8));
+                    if (p == 0) { a.scale[plane] = sc; a.shift[plane] = shf; }
+                    coef[0] = mean; coef[1] = sc; coef[2] = shf;
+                    // the wait is over: only now may this CTA hold the ticket of another item (its latency hides under pass 2)
+                    *next_id = (long long)atomicAdd(a.queue, 1ull);
+                }
+}
+
+struct PairShared {
+    Scratch scratch;
+    long long next_id;
+    float coef[4];                           // mu, scale, shift
+    unsigned short order[kPairMaxN];
+    int next_of[kPairMaxN];
+};
+
+template <typename T, int VEC, int VPT>
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
+fwd_pair_kernel(const T* __restrict__ x, T* __restrict__ y, PairArgs a) {
+    __shared__ PairShared sh;
+    constexpr int G = kThreads;
+    constexpr int kTail = VPT > 1 ? VPT / 2 : 1;     // loads in flight per thread in the ragged end of a piece
+    const int t = threadIdx.x, lane = t & 31;
+    const int P = a.pieces;
+    const uint64_t pol1 = make_policy(a.pol_first), pol2 = make_policy(a.pol_second), pol_out = make_policy(a.pol_out);
+    const unsigned int tag = *(volatile unsigned int*)a.epoch + 1u;      // advanced by the last CTA out, after every CTA has read it
+    const bool multi = a.pt.world > 1;
+    const int lo = a.row_offset, NG = a.n_global;
+    uint2* ll_mine = a.ll;
+    size_t ll_words = 0;
+    if (multi) {
+        ll_words = (size_t)NG * 2 * a.C;
+        ll_mine = reinterpret_cast<uint2*>(a.pt.peers[a.pt.rank]) + (tag & 1u) * ll_words;
+    }
+    if (a.use_order) {
+        // samples in cycle order of perm: n0, perm[n0], perm[perm[n0]], ... -- the plane an item waits for is the next in order
+        for (int i = t; i < a.N; i += G) sh.next_of[i] = (int)a.perm[lo + i] - lo;
+        __syncthreads();
+        if (t == 0) {
+            int k = 0;
+            unsigned int seen[kPairMaxN / 32];
+#pragma unroll
+            for (int w = 0; w < kPairMaxN / 32; ++w) seen[w] = 0u;
+            for (int s0 = 0; s0 < a.N; ++s0) {
+                int n = s0;
+                while (!((seen[n >> 5] >> (n & 31)) & 1u)) {
+                    seen[n >> 5] |= 1u << (n & 31);
+                    sh.order[k++] = (unsigned short)n;
+                    n = sh.next_of[n];
+                }
+            }
+        }
+    }
+    if (t == 0) sh.next_id = (long long)atomicAdd(a.queue, 1ull);
+    if (multi && tag > 1u && t < 32) {
+        // Flow control for the two-parity inboxes: this launch overwrites the words of launch tag-2.  A peer that has published
+        // anything in launch tag-1 has finished launch tag-2: wait for one word of launch tag-1 from each peer (its first row,
+        // last channel -- every exchange kernel publishes it) before the first push.
+        const uint2* prev_inbox = reinterpret_cast<const uint2*>(a.pt.peers[a.pt.rank]) + ((tag - 1u) & 1u) * ll_words;
+        for (int r = lane; r < a.pt.world; r += 32) {
+            if (r == a.pt.rank) continue;
+            const uint2* src = prev_inbox + ((size_t)(r * a.N) * 2) * a.C + (a.C - 1);
+            const long long t0 = clock64();
+            for (;;) {
+                unsigned int bits, got;
+                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(bits), "=r"(got) : "l"(src) : "memory");
+                if ((int)(got - (tag - 1u)) >= 0) break;
+                __nanosleep(100);
+                if (clock64() - t0 > kPairSpinPeer) pair_fail(a.error);
+            }
+        }
+    }
+    __syncthreads();
+    long long id = sh.next_id;
+    const int per_channel = a.N * P;
+    while (id < a.total_items) {
+        const int c = (int)(id / per_channel);
+        const int r0 = (int)(id - (long long)c * per_channel);
+        const int k = r0 / P, p = r0 - k * P;
+        const int n = a.use_order ? (int)sh.order[k] : k;
+        const int64_t plane = (int64_t)n * a.C + c;
+        Piece pc;
+        pc.plane = plane;
+        pc.v0 = p * a.piece_vecs;
+        pc.v1 = min(a.nvec, pc.v0 + a.piece_vecs);
+        const Batches<G, VPT> bt(pc, false);
+        const T* base = x + plane * a.M;
+        // ---------------- pass 1: moments of the piece (the arithmetic of stats_nchw_kernel) ----------------
+        const float K = to_f32<T>(__ldg(base));
+        Moments acc{0.f, 0.f, 0.f};
+        for (int b = 0; b < bt.full; ++b) {
+            const T* ptr = base + (int64_t)(bt.begin(b) + t) * VEC;
+            float val[VPT][VEC];
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(ptr + (int64_t)j * G * VEC, val[j], pol1);
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < VPT; ++j)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { val[j][e] -= K; s += val[j][e]; }
+            Moments bm;
+            bm.n = (float)(VPT * VEC);
+            bm.mean = s * (1.0f / (float)(VPT * VEC));
+            float qq = 0.f;
+#pragma unroll
+            for (int j = 0; j < VPT; ++j)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { const float d = val[j][e] - bm.mean; qq = fmaf(d, d, qq); }
+            bm.m2 = qq;
+            acc = merge_fast(acc, bm);
+        }
+        if (bt.rem) {
+            // the ragged end of the piece (< G*VPT vectors) as ONE predicated round: all its loads are in flight together
+            const int rhi = bt.ragged_hi();
+            for (int rlo = bt.ragged_lo() + t; rlo < rhi; rlo += kTail * G) {
+            float val[kTail][VEC];
+#pragma unroll
+            for (int j = 0; j < kTail; ++j)
+                if (rlo + j * G < rhi) Vec<T, VEC>::load(base + (int64_t)(rlo + j * G) * VEC, val[j], pol1);
+#pragma unroll
+            for (int j = 0; j < kTail; ++j) {
+                if (rlo + j * G < rhi) {                     // each vector is its own mini-batch
+                    float s = 0.f;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) { val[j][e] -= K; s += val[j][e]; }
+                    Moments bm;
+                    bm.n = (float)VEC;
+                    bm.mean = s * (1.0f / (float)VEC);
+                    float qq = 0.f;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) { const float d = val[j][e] - bm.mean; qq = fmaf(d, d, qq); }
+                    bm.m2 = qq;
+                    acc = merge_fast(acc, bm);
+                }
+            }
+            }
+        }
+        Moments m = group_merge<G>(acc, sh.scratch);             // valid in every thread
+        // ---------------- publish / partner: warp 0 ----------------
+        if (t < 32) pair_resolve<VEC>(a, m, K, c, n, p, tag, ll_mine, ll_words, sh.coef, &sh.next_id);
+        __syncthreads();
+        const float mu0 = sh.coef[0], sc = sh.coef[1], shf = sh.coef[2];
+        const long long next = sh.next_id;
+        // ---------------- pass 2: the same piece again (L2), y out ----------------
+        T* dst = y + plane * a.M;
+        for (int b = 0; b < bt.full; ++b) {
+            const int64_t o = (int64_t)(bt.begin(b) + t) * VEC;
+            float val[VPT][VEC];
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(base + o + (int64_t)j * G * VEC, val[j], pol2);
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) val[j][e] = fmaf(val[j][e] - mu0, sc, shf);
+                Vec<T, VEC>::store(dst + o + (int64_t)j * G * VEC, val[j], pol_out);
+            }
+        }
+        if (bt.rem) {
+            const int rhi = bt.ragged_hi();
+            for (int rlo = bt.ragged_lo() + t; rlo < rhi; rlo += kTail * G) {
+                float val[kTail][VEC];
+#pragma unroll
+                for (int j = 0; j < kTail; ++j)
+                    if (rlo + j * G < rhi) Vec<T, VEC>::load(base + (int64_t)(rlo + j * G) * VEC, val[j], pol2);
+#pragma unroll
+                for (int j = 0; j < kTail; ++j) {
+                    if (rlo + j * G < rhi) {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) val[j][e] = fmaf(val[j][e] - mu0, sc, shf);
+                        Vec<T, VEC>::store(dst + (int64_t)(rlo + j * G) * VEC, val[j], pol_out);
+                    }
+                }
+            }
+        }
+        id = next;                             // coef / next_id are rewritten only after the next item's block reduction (two barriers)
+    }
+    // ---- the last CTA out closes the launch: ticket counter back to zero, launch counter advanced ----
+    if (t == 0) {
+        __threadfence();
+        if (atomicAdd(a.done, 1u) == gridDim.x - 1u) {
+            *a.done = 0u;
+            *a.queue = 0ull;
+            *a.epoch = tag;
+            __threadfence();
+        }
+    }
+}
+
+}  // namespace ms

@@ -248,16 +248,115 @@ inline ResidentPlan make_resident_plan(int N, int C, int64_t M, int dtype, int a
     return r;
 }
 
+// ---- cluster-resident forward (cluster_fwd.cuh): a plane split over a thread-block cluster, S stages per CTA ----
+constexpr int kClusterCtrlBytes = 16384;                     // == kClCtrlBytes
+constexpr int kClusterMaxStages = 6;                         // == kClMaxStages
+constexpr int kClusterMaxChunks = 16;                        // == kClMaxChunks
+constexpr int kClusterChunkUnit = 8192;                      // apply warps: 256 threads x 16 B x 2 in flight
+constexpr int kClusterMinPlaneBytes = 16 * 1024;
+constexpr int kClusterMaxN = 1024;                           // == kClMaxN
+
+constexpr int kClusterMaxPieces = 32;                        // == kClMaxPieces
+constexpr int kClusterMinPartBytes = 16 * 1024;              // a CTA's share of a piece is at least this (P > 1 or CS > 1)
+constexpr int kClusterStdRows = 512;                         // first forward: rows a coordinator warp keeps in registers (32 x kClStdRows)
+
+struct ClusterPlan {
+    bool ok;
+    int cluster, pieces, stages, plane_bytes, part_bytes, part_stride, chunk_bytes, chunks, smem;
+};
+
+// Geometry for planes cut into `pieces` pieces, each held by a cluster of `cs` CTAs (1, 2, 4 or 8); `max_stages` caps S.
+inline ClusterPlan make_cluster_plan(int64_t M, int dtype, int align, int cs, int pieces, int max_stages = kClusterMaxStages) {
+    ClusterPlan c{};
+    const int64_t pb = M * elem_size(dtype);
+    if (align < 16 || pb % 16 != 0 || pb < kClusterMinPlaneBytes || pb > 0x7fffffff) return c;
+    if (pieces < 1 || pieces > kClusterMaxPieces) return c;
+    const int64_t shares = (int64_t)cs * pieces;
+    const int64_t part = ceil_div(ceil_div(pb, shares), 16) * 16;
+    if (shares > 1 && part < kClusterMinPartBytes) return c;
+    if ((int64_t)(pieces - 1) * cs * part >= pb) return c;    // the last piece holds something
+    const int64_t stride = ceil_div(part, 128) * 128;
+    int64_t stages = (kResidentMaxSmem - kClusterCtrlBytes) / stride;
+    if (stages < 1) return c;
+    if (stages > kClusterMaxStages) stages = kClusterMaxStages;
+    if (stages > max_stages) stages = max_stages;
+    const int64_t chunk = kClusterChunkUnit * ceil_div(part, (int64_t)kClusterChunkUnit * kClusterMaxChunks);
+    c.cluster = cs;
+    c.pieces = pieces;
+    c.stages = (int)stages;
+    c.plane_bytes = (int)pb;
+    c.part_bytes = (int)part;
+    c.part_stride = (int)stride;
+    c.chunk_bytes = (int)chunk;
+    c.chunks = (int)ceil_div(part, chunk);
+    c.smem = (int)(kClusterCtrlBytes + stages * stride);
+    c.ok = true;
+    return c;
+}
+
+// most pieces make_cluster_plan() accepts for this plane size (sizes the piece table of the workspace)
+inline int cluster_max_pieces(int64_t M, int dtype) {
+    const int64_t pb = M * elem_size(dtype);
+    int64_t p = pb / kClusterMinPartBytes;
+    if (p < 1) p = 1;
+    return (int)(p > kClusterMaxPieces ? kClusterMaxPieces : p);
+}
+
+// ---- paired forward (pair_fwd.cuh): a CTA owns a piece of a plane for both of its passes ----------------------
+constexpr int kPairMaxPieces = 32;
+constexpr int64_t kPairPieceBytes = 112 * 1024;              // largest piece: 592 CTAs x 112 KB live in L2 between the passes
+constexpr int64_t kPairMinPlaneBytes = 8 * 1024;
+
+struct PairPlan {
+    bool ok;
+    int vec, vpt, nvec, pieces, piece_vecs;
+};
+
+inline PairPlan make_pair_plan(int64_t M, int dtype, int align, int force_pieces = 0) {
+    static const int64_t piece_bytes = env_or("MAXSTYLE_PAIR_PIECE_KB", kPairPieceBytes, 1024);
+    PairPlan p{};
+    const int es = elem_size(dtype);
+    if (align >= 32 && (M * es) % 32 == 0) p.vec = 32 / es;
+    else if (align >= 16 && (M * es) % 16 == 0) p.vec = 16 / es;
+    else return p;
+    const int64_t nvec = M / p.vec, pb = M * es;
+    if (pb < kPairMinPlaneBytes || nvec > 0x7fffffff) return p;
+    p.nvec = (int)nvec;
+    p.vpt = vpt_one_tensor(p.vec);
+    int64_t P = force_pieces;
+    if (P <= 0) {
+        // A piece costs ceil(vectors / round) latency rounds of 256 x vpt vectors plus ~1.5 rounds of publish / partner gap, and
+        // must stay small enough for 592 of them to live in L2 between their two passes: the fewest pieces of at most
+        // `piece_bytes` (~112 KB), then the cheapest of the next few counts.
+        const int64_t round = (int64_t)kThreadsPerBlock * p.vpt;
+        const int64_t first = ceil_div(pb, piece_bytes);
+        double best = 0.0;
+        for (int64_t cand = first; cand <= first + 3 && cand <= kPairMaxPieces; ++cand) {
+            const int64_t pv = ceil_div(nvec, cand);
+            const double cost = (double)ceil_div(nvec, pv) * ((double)ceil_div(pv, round) + 1.5);
+            if (P <= 0 || cost < best) { P = cand; best = cost; }
+        }
+    }
+    const int64_t pv = ceil_div(nvec, P);
+    P = ceil_div(nvec, pv);                                   // no empty pieces
+    p.pieces = (int)P;
+    p.piece_vecs = (int)pv;
+    p.ok = true;
+    return p;
+}
+
 // Workspace layout (bytes):  [plane tickets: planes x u64][sample tickets: N x u64]
 //                            [done counter: 256 B][partials: planes x slots_bound x float4]
 //                            [fused forward: error flag + queue + done 256 B][arrived | ready: 2 x C x u32][item partials]
 //                            [resident forward: plane ready flags, planes x u32]
+//                            [cluster forward: {value, tag} words, planes x 2 x 8 B][piece words, planes x max pieces x 2 x 8 B]
+//                            (its launch counter: u32 @24 of the error block)
 // slots_bound covers every plan make_plan() can produce for this shape:
 //   slots = ceil(nvec/per) + 1  with  per >= total/kMaxGrid  =>  slots <= kMaxGrid/planes + 2.
 // NHWC (layout 1): the shared unit is the sample, each CTA publishes C partials for it (make_plan_nhwc).
 struct Workspace {
-    size_t plane_tickets, sample_tickets, done_counter, partials, res_error, res_flags, res_partials, plane_ready, total;
-    int slots_bound;
+    size_t plane_tickets, sample_tickets, done_counter, partials, res_error, res_flags, res_partials, plane_ready, cl_words, cl_pieces, total;
+    int slots_bound, max_pieces;
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -285,10 +384,20 @@ inline Workspace workspace_layout(int N, int C, int64_t M, int dtype, int layout
         const RingPlan rp = make_ring_plan(N, C, M, dtype, 16);
         if (rp.ok && (int64_t)C * rp.items_per_channel > items) items = (int64_t)C * rp.items_per_channel;
     }
-    w.res_error = off; off += 256;                           // int error @0, u64 queue @8, u32 done @16
+    w.res_error = off; off += 256;                           // int error @0, u64 queue @8, u32 done @16, u32 cluster launch counter @24
     w.res_flags = off; off = align_up(off + (size_t)2 * C * sizeof(uint32_t), 256);
     w.res_partials = off; off = align_up(off + (size_t)items * 16, 256);
     w.plane_ready = off; off = align_up(off + (size_t)planes * sizeof(uint32_t), 256);
+    w.cl_words = off; off = align_up(off + (size_t)planes * 2 * 8, 256);
+    {
+        int mp = cluster_max_pieces(M, dtype);               // the piece table serves the cluster and the paired forward
+        if (mp < kPairMaxPieces && M * elem_size(dtype) >= kPairMinPlaneBytes) {
+            const int64_t want = ceil_div(M * elem_size(dtype), 8 * 1024);
+            mp = (int)(want > kPairMaxPieces ? kPairMaxPieces : (want > mp ? want : mp));
+        }
+        w.cl_pieces = off; off = align_up(off + (size_t)planes * mp * 2 * 8, 256);
+        w.max_pieces = mp;
+    }
     w.total = off;
     return w;
 }

@@ -514,9 +514,12 @@ def test_resident_forward_flag_variants_and_fixed_points():
 def test_fused_forward_declines_what_it_cannot_hold():
     from maxstyle_b200 import _lib as L
     lib = L.get_lib()
-    assert lib.maxstyle_fwd_kernels(256, 32, 512, 512, 0, 0, 0) == 3      # config 5: one channel is 256 MB, no L2 window
+    old = L.SWEEP_NO_PAIR                                                 # the L2-window / resident kernels' own limits
+    assert lib.maxstyle_fwd_kernels(256, 32, 512, 512, 0, 0, old) == 3    # config 5: one channel is 256 MB, no L2 window
+    assert lib.maxstyle_fwd_kernels(256, 32, 512, 512, 0, 0, 0) == 1      # ... the paired kernel takes it (cycle-ordered walk)
     assert lib.maxstyle_fwd_kernels(6, 2, 37, 41, 0, 0, 0) == 3           # planes not a multiple of 16 bytes
     assert lib.maxstyle_fwd_kernels(64, 8, 28, 28, 0, 0, 0) == 3          # 3 KB planes: warp-per-plane kernels
     assert lib.maxstyle_fwd_kernels(20, 64, 224, 224, 0, 0, L.SWEEP_NO_FUSED) == 3
-    assert lib.maxstyle_fwd_kernels(512, 64, 112, 112, 1, 0, 0) == 3      # N > co-resident CTAs and a 12.8 MB channel: two-pass
+    assert lib.maxstyle_fwd_kernels(512, 64, 112, 112, 1, 0, old) == 3    # N > co-resident CTAs and a 12.8 MB channel: two-pass
+    assert lib.maxstyle_fwd_kernels(512, 64, 112, 112, 1, 0, 0) == 1
     assert lib.maxstyle_fwd_kernels(512, 64, 112, 112, 1, 0, L.SWEEP_NO_RING | L.SWEEP_FORCE_WINDOW) == 1
