@@ -244,7 +244,8 @@ int maxstyle_bwd(const void* dy, const void* x, void* dx,
  * style-optimisation loop (replaces cross_entropy_2D, src/models/custom_loss.py:1043-1105, label-map branch :1069-1078):
  *   loss = -(1/D) sum_p mask[p] * weight[t_p] * log_softmax(logits[:, :, p])[t_p],  D = N*H*W if size_average else 1.
  * `weight` ([C], already normalised by the caller as the reference does: w / sum(w) * C) and `mask` ([N*H*W]) may be NULL.
- * Labels equal to -100 are ignored (F.nll_loss's default ignore_index, inherited by the reference).  One kernel each way;
+ * Labels equal to -100 are ignored (F.nll_loss's default ignore_index, inherited by the reference); any other label outside
+ * [0, C) stops the kernel with a device-side trap (the reference's F.nll_loss raises a device assert).  One kernel each way;
  * the forward's sum is deterministic.  `workspace`: maxstyle_ce2d_workspace_bytes() bytes, 256-byte aligned, zero-filled once.
  * The backward takes the upstream gradient of the scalar loss from device memory (`dloss`, 1 float). */
 size_t maxstyle_ce2d_workspace_bytes(int N, int C, int H, int W);
@@ -253,6 +254,19 @@ int maxstyle_ce2d_fwd(const void* logits, const int64_t* target, const float* we
                       maxstyle_stream_t stream);
 int maxstyle_ce2d_bwd(const void* logits, const int64_t* target, const float* weight, const float* mask, const float* dloss,
                       void* dlogits, int N, int C, int H, int W, int dtype, int size_average, maxstyle_stream_t stream);
+
+/* The same loss AND its gradient in ONE kernel (the inner loop always back-propagates it: model:555-561), both branches of
+ * cross_entropy_2D: a label map (`labels`, int64 [N,H,W]; custom_loss.py:1069-1078) or a soft target (`soft_target`,
+ * [N,C,H,W] of the logits' dtype; logits unless `soft_is_probability`; custom_loss.py:1079-1102) -- exactly one of the two.
+ * `dlogits` (optional) receives d loss / d logits and `dsoft_target` (optional, soft branch) d loss / d target, both for an upstream
+ * gradient of 1; maxstyle_ce2d_scale multiplies a gradient by the actual upstream gradient, read from device memory.
+ * C <= 8 (more: MAXSTYLE_ERR_UNSUPPORTED, use maxstyle_ce2d_fwd / _bwd).  A label outside [0, C) other than -100 stops the
+ * kernel with a device-side trap, as F.nll_loss's device assert does in the reference. */
+int maxstyle_ce2d_fwd_grad(const void* logits, const int64_t* labels, const void* soft_target, int soft_is_probability,
+                           const float* weight, const float* mask, float* loss, void* dlogits, void* dsoft_target,
+                           int N, int C, int H, int W, int dtype, int size_average, void* workspace, size_t workspace_bytes,
+                           maxstyle_stream_t stream);
+int maxstyle_ce2d_scale(void* grad, const float* scale, int64_t count, int dtype, maxstyle_stream_t stream);
 
 /* Stand-alone optimiser step on the three parameter tensors (same arithmetic as the fused
  * epilogue; used when the gradients arrive through autograd's .grad instead). */

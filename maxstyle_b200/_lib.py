@@ -72,6 +72,9 @@ SIGNATURES = {
     "maxstyle_ce2d_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "maxstyle_ce2d_fwd": (C.c_int, [_vp, _vp, _f32p, _f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
     "maxstyle_ce2d_bwd": (C.c_int, [_vp, _vp, _f32p, _f32p, _f32p, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "maxstyle_ce2d_fwd_grad": (C.c_int, [_vp, _vp, _vp, C.c_int, _f32p, _f32p, _f32p, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, _vp, C.c_size_t, _vp]),
+    "maxstyle_ce2d_scale": (C.c_int, [_vp, _f32p, C.c_int64, C.c_int, _vp]),
     "maxstyle_step": (C.c_int, [_f32p, _f32p, _f32p, C.POINTER(StepStruct), C.c_int, C.c_int, _vp]),
 }
 

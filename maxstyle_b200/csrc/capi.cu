@@ -539,7 +539,12 @@ int try_cluster_fwd(const FwdCall& f, const Workspace& w, int sms, int sweep) {
 // ---- paired forward -----------------------------------------------------------------------------------
 template <typename T, int VEC>
 void launch_pair(const FwdCall& f, const PairArgs& a, int grid) {
-    fwd_pair_kernel<T, VEC, vpt_for<VEC, 1>()><<<grid, kThreads, 0, f.stream>>>(static_cast<const T*>(f.x), static_cast<T*>(f.y), a);
+    static const int64_t minb = env_or("MAXSTYLE_PAIR_MINB", 4, 1);      // CTAs per SM the register budget is set for (3: 85 registers, 4: 64)
+    const T* xs = static_cast<const T*>(f.x);
+    T* ys = static_cast<T*>(f.y);
+    constexpr int VPT = vpt_for<VEC, 1>();
+    if (minb == 3) fwd_pair_kernel<T, VEC, VPT, 3><<<grid, kThreads, 0, f.stream>>>(xs, ys, a);
+    else fwd_pair_kernel<T, VEC, VPT, 4><<<grid, kThreads, 0, f.stream>>>(xs, ys, a);
 }
 
 struct PairChoice { PairPlan plan; int grid; int use_order; };
@@ -549,14 +554,24 @@ PairChoice choose_pair(int N, int C, int64_t M, int dtype, int align, int sms, i
     const int force_pieces = (sweep >> MAXSTYLE_SWEEP_CLUSTER_PIECES_SHIFT) & 63;
     ch.plan = make_pair_plan(M, dtype, align, force_pieces);
     if (!ch.plan.ok) return ch;
-    const int64_t items = (int64_t)N * C * ch.plan.pieces, cap = (int64_t)sms * kBlocksPerSM;
+    static const int64_t minb = env_or("MAXSTYLE_PAIR_MINB", 4, 1);
+    const int64_t items = (int64_t)N * C * ch.plan.pieces, cap = (int64_t)sms * (minb == 3 ? 3 : 4);
     ch.grid = (int)(items < cap ? items : cap);
     // an item waits for items within W positions: grid > W keeps a CTA free for the lowest missing one
     if ((int64_t)N * ch.plan.pieces >= ch.grid && (has_partner || whole_channel)) {
         if (whole_channel || N > kPairMaxN || 2 * ch.plan.pieces >= ch.grid) { ch.plan.ok = false; return ch; }
         ch.use_order = 1;
     }
+    // experiment: walk the samples in cycle order whenever it is allowed (partner planes are then taken back to back)
+    static const int64_t force_order = env_or("MAXSTYLE_PAIR_ORDER", 0, 1);
+    if (force_order == 1 && !whole_channel && has_partner && N <= kPairMaxN && 2 * ch.plan.pieces < ch.grid) ch.use_order = 1;
     return ch;
+}
+
+// Where the paired kernel is the default: tensors that do not sit comfortably in L2 anyway (>= 16 MB); smaller ones are
+// launch-latency-bound and the window / two-pass paths measured as fast or faster (profiles/r02_fwd_paths.txt).
+bool pair_preferred(int N, int C, int64_t M, int dtype) {
+    return (int64_t)N * C * M * elem_size(dtype) >= (16ll << 20);
 }
 
 // Same contract as try_fused_fwd.
@@ -582,7 +597,8 @@ int try_pair_fwd(const FwdCall& f, const Workspace& w, int sms, int sweep) {
     a.gamma_std = f.gamma_std; a.beta_std = f.beta_std;
     a.ll = reinterpret_cast<uint2*>(f.ws + w.cl_words);
     a.piece_ll = reinterpret_cast<uint2*>(f.ws + w.cl_pieces);
-    a.epoch = multi ? f.pt.epoch : reinterpret_cast<unsigned int*>(f.ws + w.res_error + 24);
+    a.wepoch = reinterpret_cast<unsigned int*>(f.ws + w.res_error + 24);
+    a.epoch = multi ? f.pt.epoch : nullptr;
     a.queue = reinterpret_cast<unsigned long long*>(f.ws + w.res_error + 8);
     a.done = reinterpret_cast<unsigned int*>(f.ws + w.res_error + 16);
     a.error = reinterpret_cast<int*>(f.ws + w.res_error);
@@ -726,7 +742,6 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
     if ((flags & MAXSTYLE_MIX_STYLE) && (!perm || !lmda)) return MAXSTYLE_ERR_BAD_ARG;
     if (!(flags & MAXSTYLE_NO_NOISE) && (!gamma_noise || !beta_noise || !gamma_std || !beta_std)) return MAXSTYLE_ERR_BAD_ARG;
     if (!(stats_sweep & MAXSTYLE_SWEEP_NO_FUSED) && (gamma_std && beta_std) && !is_nhwc(layout, C)) {
-        // x read from HBM once: ordered statistics/apply items with the window between them held in L2 (fused_fwd.cuh)
         const int64_t M = (int64_t)H * W;
         const Workspace w = workspace_layout(N, C, M, dtype);
         if ((rc = check_workspace(workspace, workspace_bytes, w))) return rc;
@@ -734,9 +749,16 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
         if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
         FwdCall f{x, y, mu, sig, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, M, dtype, flags, eps,
                   static_cast<char*>(workspace), static_cast<cudaStream_t>(stream), N, 0, C, PeerTables{}};
+        // Five single-kernel forwards, each the default where it measured fastest (profiles/r02_fwd_paths.txt):
+        //   resident  planes of 16-108 KB, tensors >= 64 MB (two CTAs share an SM)               -- x crosses L2 -> SM once
+        //   paired    steady state (cached batch std), tensors >= 16 MB, any plane >= 8 KB     -- piece re-read from L2 microseconds later
+        //   window    the first forward of a module (whole-channel dependency), planes >= 64 KB -- ordered queue, 32 MB L2 window
+        //   ring / cluster: only when forced (tests, experiments)
         const int force_other = stats_sweep & (MAXSTYLE_SWEEP_FORCE_RESIDENT | MAXSTYLE_SWEEP_FORCE_RING | MAXSTYLE_SWEEP_FORCE_WINDOW);
         const int force_any = force_other | (stats_sweep & (MAXSTYLE_SWEEP_FORCE_CLUSTER | MAXSTYLE_SWEEP_FORCE_PAIR));
-        if (!(stats_sweep & MAXSTYLE_SWEEP_NO_PAIR) && (!force_any || (stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR))) {
+        const bool first = (flags & MAXSTYLE_COMPUTE_BATCH_STD) != 0;
+        const bool pair_allowed = !(stats_sweep & MAXSTYLE_SWEEP_NO_PAIR) && (!force_any || (stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR));
+        if (stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR) {
             rc = try_pair_fwd(f, w, sms, stats_sweep);
             if (rc >= 0) return rc;
         }
@@ -748,12 +770,20 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
             rc = try_resident_fwd(f, w, sms, stats_sweep, apply_sweep, (stats_sweep & MAXSTYLE_SWEEP_FORCE_RESIDENT) != 0);
             if (rc >= 0) return rc;
         }
+        if (pair_allowed && !first && pair_preferred(N, C, M, dtype)) {
+            rc = try_pair_fwd(f, w, sms, stats_sweep);
+            if (rc >= 0) return rc;
+        }
         if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RING)) {
             rc = try_ring_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_RING) != 0, (stats_sweep & MAXSTYLE_SWEEP_X_KEEP) != 0);
             if (rc >= 0) return rc;
         }
         rc = try_fused_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW) != 0, (stats_sweep & MAXSTYLE_SWEEP_X_KEEP) != 0);
         if (rc >= 0) return rc;
+        if (pair_allowed && first && pair_preferred(N, C, M, dtype)) {          // first forward, no window: still one read of x
+            rc = try_pair_fwd(f, w, sms, stats_sweep);
+            if (rc >= 0) return rc;
+        }
     }
     rc = maxstyle_stats(x, mu, sig, C, 0, N, C, H, W, dtype, layout, eps, stats_sweep, workspace, workspace_bytes, stream);
     if (rc) return rc;
@@ -796,6 +826,9 @@ int maxstyle_fwd_p2p(const void* x, void* y, float* mu_all, float* sig_all, int 
         rc = try_cluster_fwd(f, w, sms, stats_sweep);
         if (rc >= 0) return rc;
     }
+    // the L2-window kernel hides the exchange behind a fixed 32 MB of streaming: beyond 2 ranks their skew outgrows it (measured
+    // slower than statistics -> exchange + tables -> apply, profiles/r01_multi.txt), so it is only taken there when forced
+    if (world > 2 && !(stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW)) return MAXSTYLE_ERR_UNSUPPORTED;
     rc = try_fused_fwd(f, w, sms, (stats_sweep & MAXSTYLE_SWEEP_FORCE_WINDOW) != 0, (stats_sweep & MAXSTYLE_SWEEP_X_KEEP) != 0);
     return rc >= 0 ? rc : MAXSTYLE_ERR_UNSUPPORTED;
 }
@@ -857,30 +890,70 @@ int maxstyle_ce2d_bwd(const void* logits, const int64_t* target, const float* we
     return check_launch();
 }
 
+int maxstyle_ce2d_fwd_grad(const void* logits, const int64_t* labels, const void* soft_target, int soft_is_probability,
+                           const float* weight, const float* mask, float* loss, void* dlogits, void* dsoft_target,
+                           int N, int C, int H, int W, int dtype, int size_average, void* workspace, size_t workspace_bytes,
+                           maxstyle_stream_t stream) {
+    if (!logits || !loss || N <= 0 || C <= 0 || H <= 0 || W <= 0) return MAXSTYLE_ERR_BAD_ARG;
+    if ((labels == nullptr) == (soft_target == nullptr)) return MAXSTYLE_ERR_BAD_ARG;      // exactly one kind of target
+    if (dsoft_target && !soft_target) return MAXSTYLE_ERR_BAD_ARG;
+    if (dtype != MAXSTYLE_F32 && dtype != MAXSTYLE_BF16) return MAXSTYLE_ERR_UNSUPPORTED;
+    if (C > kCeMaxC) return MAXSTYLE_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < maxstyle_ce2d_workspace_bytes(N, C, H, W) || (reinterpret_cast<uintptr_t>(workspace) & 255u))
+        return MAXSTYLE_ERR_WORKSPACE;
+    const int sms = sm_count();
+    if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+    const int64_t hw = (int64_t)H * W, P = (int64_t)N * hw;
+    int grid = ce2d_grid(P, sms);
+    if (grid > 148 * 8 * 2) grid = 148 * 8 * 2;
+    const float inv = size_average ? 1.0f / (float)P : 1.0f;
+    unsigned int* counter = static_cast<unsigned int*>(workspace);
+    float* partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long* lab = reinterpret_cast<const long long*>(labels);
+    if (dtype == MAXSTYLE_F32)
+        ce2d_fused_kernel<float, kCeMaxC><<<grid, kCeThreads, 0, s>>>(static_cast<const float*>(logits), lab, static_cast<const float*>(soft_target),
+                                                                     soft_is_probability, weight, mask, loss, static_cast<float*>(dlogits),
+                                                                     static_cast<float*>(dsoft_target), partials, counter, P, hw, C, inv);
+    else
+        ce2d_fused_kernel<__nv_bfloat16, kCeMaxC><<<grid, kCeThreads, 0, s>>>(
+            static_cast<const __nv_bfloat16*>(logits), lab, static_cast<const __nv_bfloat16*>(soft_target), soft_is_probability, weight, mask,
+            loss, static_cast<__nv_bfloat16*>(dlogits), static_cast<__nv_bfloat16*>(dsoft_target), partials, counter, P, hw, C, inv);
+    return check_launch();
+}
+
+int maxstyle_ce2d_scale(void* grad, const float* scale, int64_t count, int dtype, maxstyle_stream_t stream) {
+    if (!grad || !scale || count <= 0) return MAXSTYLE_ERR_BAD_ARG;
+    if (dtype != MAXSTYLE_F32 && dtype != MAXSTYLE_BF16) return MAXSTYLE_ERR_UNSUPPORTED;
+    const int sms = sm_count();
+    if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+    const int64_t want = (count + 256 * 4 - 1) / (256 * 4), cap = (int64_t)sms * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == MAXSTYLE_F32) ce2d_scale_kernel<float><<<grid, 256, 0, s>>>(static_cast<float*>(grad), scale, count);
+    else ce2d_scale_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(grad), scale, count);
+    return check_launch();
+}
+
 int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int stats_sweep) {
     if (check_shape(N, C, H, W, dtype, layout) != MAXSTYLE_OK) return 0;
     if ((stats_sweep & MAXSTYLE_SWEEP_NO_FUSED) || is_nhwc(layout, C)) return 3;
     const int64_t M = (int64_t)H * W;
     const int force_other = stats_sweep & (MAXSTYLE_SWEEP_FORCE_RESIDENT | MAXSTYLE_SWEEP_FORCE_RING | MAXSTYLE_SWEEP_FORCE_WINDOW);
     const int force_any = force_other | (stats_sweep & (MAXSTYLE_SWEEP_FORCE_CLUSTER | MAXSTYLE_SWEEP_FORCE_PAIR));
-    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_PAIR) && (!force_any || (stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR)) && N >= 2) {
+    auto pair_ok = [&]() {
         static const int64_t pair_enabled = env_or("MAXSTYLE_PAIR", 1, 1);
-        if ((stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR) || pair_enabled == 1) {
-            const PairChoice ch = choose_pair(N, C, M, dtype, 32, sm_count(), stats_sweep, false, true);
-            if (ch.plan.ok && ch.plan.pieces <= workspace_layout(N, C, M, dtype).max_pieces) return 1;
-        }
-    }
+        if (N < 2 || (!(stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR) && pair_enabled != 1)) return false;
+        const PairChoice ch = choose_pair(N, C, M, dtype, 32, sm_count(), stats_sweep, false, true);
+        return ch.plan.ok && ch.plan.pieces <= workspace_layout(N, C, M, dtype).max_pieces;
+    };
+    if ((stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR) && pair_ok()) return 1;
     if (!(stats_sweep & MAXSTYLE_SWEEP_NO_CLUSTER) && (stats_sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER) && N >= 2 &&
         M * elem_size(dtype) >= kClusterMinPlaneBytes) {
-        // steady state (cached batch std): the first forward of a module may take another path when N exceeds the clusters
-        static const int64_t enabled = env_or("MAXSTYLE_CLUSTER", 1, 1);
-        const bool force = (stats_sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER) != 0;
-        if (force || enabled == 1) {
-            const ClusterNeeds need{N, false, true};
-            const ClusterChoice ch = dtype == MAXSTYLE_F32 ? choose_cluster<float>((int64_t)N * C, M, dtype, 32, sm_count(), stats_sweep, need)
-                                                           : choose_cluster<__nv_bfloat16>((int64_t)N * C, M, dtype, 32, sm_count(), stats_sweep, need);
-            if (ch.plan.ok && ch.clusters > 0) return 1;
-        }
+        const ClusterNeeds need{N, false, true};
+        const ClusterChoice ch = dtype == MAXSTYLE_F32 ? choose_cluster<float>((int64_t)N * C, M, dtype, 32, sm_count(), stats_sweep, need)
+                                                       : choose_cluster<__nv_bfloat16>((int64_t)N * C, M, dtype, 32, sm_count(), stats_sweep, need);
+        if (ch.plan.ok && ch.clusters > 0) return 1;
     }
     if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RESIDENT)) {
         const ResidentPlan rp = make_resident_plan(N, C, M, dtype, 32);
@@ -896,6 +969,7 @@ int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int 
             if (k > 0 && N <= (items < cap ? items : cap)) return 1;
         }
     }
+    if (!(stats_sweep & MAXSTYLE_SWEEP_NO_PAIR) && !force_any && pair_preferred(N, C, M, dtype) && pair_ok()) return 1;
     if (!(stats_sweep & MAXSTYLE_SWEEP_NO_RING)) {
         const RingPlan gp = make_ring_plan(N, C, M, dtype, 32);
         if (gp.ok && (gp.profitable || (stats_sweep & MAXSTYLE_SWEEP_FORCE_RING))) return 1;

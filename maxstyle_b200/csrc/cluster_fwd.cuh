@@ -114,11 +114,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 }
 // A wait that gave up means a broken launch (a peer rank died, the grid is not co-resident): results would be
 // wrong, so the kernel raises the error word and traps -- the CUDA error reaches the host at its next call.
-__device__ __forceinline__ void cl_fail(int* error) {
-    *error = 1;
-    __threadfence_system();
-    __trap();
-}
+__device__ __forceinline__ void cl_fail(int* error) { wait_timed_out(error); }
 __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity, int* error) {
     if (mbar_try_wait_cluster(bar, parity)) return;
     const long long t0 = clock64();

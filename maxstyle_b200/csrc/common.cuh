@@ -242,6 +242,16 @@ __device__ __forceinline__ bool ticket_add(unsigned long long* counter, unsigned
     return last;
 }
 
+// A bounded device-side wait that gave up means a broken launch (a peer rank died or is more than the bound late, the grid
+// is not co-resident): carrying on would produce wrong statistics silently.  Raise the caller's error word (readable through
+// maxstyle_workspace_status / PeerTableExchange.check) and trap -- the CUDA error surfaces at the host's next call, the way a
+// hung NCCL collective ends in an error instead of a wrong answer.
+__device__ __forceinline__ void wait_timed_out(int* error) {
+    if (error != nullptr) *error = 1;
+    __threadfence_system();
+    __trap();
+}
+
 // Broadcast a flag computed by the group's first thread to the whole group.
 template <int G> __device__ __forceinline__ bool group_bcast(bool flag, Scratch& s) {
     if constexpr (G > 32) {

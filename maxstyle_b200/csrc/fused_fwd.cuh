@@ -165,7 +165,7 @@ __device__ __forceinline__ void fused_finalize_channel(const FusedArgs& a, int c
             float m = 0.f, sg = 0.f;
             const long long t0 = clock64();
             while (!(ld_ll(src, epoch, m) & ld_ll(src + C, epoch, sg))) {
-                if (clock64() - t0 > 2 * kFusedSpinLimit) { *a.error = 1; break; }
+                if (clock64() - t0 > 20 * kFusedSpinLimit) wait_timed_out(a.error);      // another rank: ~20 s
             }
             fin_mu[row] = m;
             fin_sig[row] = sg;
@@ -273,7 +273,7 @@ fwd_fused_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a) {
                         const long long t0 = clock64();
                         while (!(ok = ld_acquire_u32(&a.ready[it.c]) != 0u)) {
                             __nanosleep(64);
-                            if (clock64() - t0 > kFusedSpinLimit) { *a.error = 1; ok = 1; break; }
+                            if (clock64() - t0 > (a.pt.world > 1 ? 20 : 1) * kFusedSpinLimit) wait_timed_out(a.error);
                         }
                     }
                 }

@@ -1,26 +1,28 @@
-// Paired forward: the whole MaxStyle forward (maxstyle.py:157-185) in ONE persistent kernel that reads x from HBM once
-// and keeps every SM streaming all the time.
+// Paired forward: the whole MaxStyle forward (maxstyle.py:157-185) in ONE persistent kernel that reads x from HBM once.
 //
 // In the steady state of the layer (gamma_std / beta_std cached, maxstyle.py:165-168) a plane depends on exactly ONE other
-// plane: its mixing partner (perm[n], same channel).  So the unit of work is a PIECE of a plane (32-64 KB) that one CTA
+// plane: its mixing partner (perm[n], same channel).  So the unit of work is a PIECE of a plane (<= ~100 KB) that one CTA
 // owns for both of its uses, back to back:
 //     pass 1   stream the piece with 256-bit loads, shifted moments (the arithmetic of stats_nchw_kernel)       [HBM -> L2 -> SM]
-//     publish  the piece's (mean, M2) as two 8-byte {value, tag} words; fetch the plane's other pieces, merge them in piece
-//              order (every owner of a piece computes the same plane statistics); the owner of piece 0 publishes (mu, sig) --
-//              and pushes them into the peers' inboxes when the batch is sharded over GPUs
-//     partner  fetch (mu, sig) of the partner plane (first forward: of the whole channel, and take the batch std)
-//     pass 2   stream the SAME piece again -- it was read a few microseconds ago and is still in L2 -- and write
+//     publish  the piece's (mean, M2) as two 8-byte {value, tag} words; fetch the plane's other pieces and merge them in piece
+//              order (every owner of a piece computes the same plane statistics); the owner of piece 0 publishes (mu, sig):
+//              table words, the fp32 tables of the backward and -- when the batch is sharded over GPUs -- every peer's inbox
+//     partner  fetch (mu, sig) of the partner plane (first forward: of the whole channel, and take the batch std); style_coeffs
+//     pass 2   stream the SAME piece again -- it was read microseconds ago and is still in L2 -- and write
 //              y = (x - mu) * A/sig + B                                                                           [L2 -> SM -> HBM]
-// 4 CTAs x 256 threads per SM run this loop out of phase, so while one CTA sits in its publish/partner gap (2-3 us of L2
-// round trips) the other three stream; the pieces live in L2 only between their two passes (592 CTAs x <= 64 KB ~ 30 MB of
-// the 126 MB), so the second read never goes to HBM.  Compared with fused_fwd.cuh (ordered statistics / apply queue with a
-// 32 MB window): no control warp, no named-barrier hand-off per item, no channel-wide finaliser on the steady-state path, and
-// the re-read follows the first read by microseconds instead of by a window of 6 channels.
+// 4 CTAs x 256 threads per SM run this loop out of phase, so while one CTA sits in its publish / partner gap (2-3 us of L2
+// round trips, warp 0 only) the other three stream; the pieces live in L2 only between their two passes (592 CTAs x <= 100 KB,
+// about what the L2 holds of such a stream: measured 16 % of the second reads miss at 59 MB, 68 % at 89 MB).  Compared with
+// fused_fwd.cuh (ordered statistics / apply queue with a 32 MB window): no control warp, no named-barrier hand-off per item, no
+// channel-wide finaliser on the steady-state path, and the re-read follows the first read by microseconds.
 // Items are taken with an atomic ticket, in order (channel-major; the pieces of a plane adjacent).  An item publishes before
-// it waits and only waits for items within W positions of it: W = N*P (whole channel: first forward / multi GPU) or 2P when
-// the samples are visited in cycle order of perm (the partner plane is then the NEXT plane).  The ticket of the next item is
-// taken only after the wait, so a CTA never parks a ticket behind a wait; with more CTAs than W some CTA is always free to
-// take the lowest missing item: no deadlock, no co-residency assumption beyond grid > W (host-side condition).
+// it waits, and waits only on publishes (its plane's pieces) or on the plane words of another plane, which that plane's
+// piece-0 owner publishes after waiting for nothing but publishes.  All of that lies within W positions of the item: W = N*P
+// (whole channel: first forward / multi GPU) or 2P when the samples are visited in cycle order of perm (the partner plane is
+// then the NEXT plane).  The ticket of the next item is taken only after the wait, so a CTA never parks a ticket behind a
+// wait; with more CTAs than W some CTA is always free to take the lowest missing item (host-side condition grid > W).
+// Variants tried and dropped: two items open per CTA, and a control warp resolving item k while seven
+// warps stream item k+1 -- both double the pieces alive in L2 and lost more to second-read misses than the hidden gap gave.
 #pragma once
 #include "common.cuh"
 #include "kernels_nchw.cuh"
@@ -53,18 +55,15 @@ struct PairArgs {
     float *gamma_std, *beta_std;
     uint2* ll;                 // [n_global][2][C] {value, tag} words (single GPU: workspace; multi GPU: the own inbox is used instead)
     uint2* piece_ll;           // [N*C][P][2]
-    unsigned int* epoch;       // launch counter the tag comes from (multi GPU: the exchange epoch)
+    unsigned int* wepoch;      // launches on this workspace: tags the words that live in it
+    unsigned int* epoch;       // multi GPU: the exchange epoch shared with the peers: tags the plane words in the inboxes
     unsigned long long* queue;
     unsigned int* done;
     int* error;
     PeerTables pt;
 };
 
-__device__ __forceinline__ void pair_fail(int* error) {
-    *error = 1;
-    __threadfence_system();
-    __trap();
-}
+__device__ __forceinline__ void pair_fail(int* error) { wait_timed_out(error); }
 __device__ __forceinline__ void st_ll_dev(void* p, float v, unsigned int tag) {
     asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }
@@ -79,298 +78,309 @@ __device__ __forceinline__ void pair_poll(const uint2* w0, const uint2* w1, unsi
     }
 }
 
-// Everything between the two passes of a piece, run by warp 0 (kept out of line so that its register needs -- the rows of a
-// channel on the first forward -- do not spill into the streaming loops): publish the piece, merge the plane, publish the
-// plane (piece 0), fetch the partner / the channel, style coefficients -> coef[0..2], then the ticket of the next item.
+struct PairShared {
+    Scratch scratch;
+    long long next_id;
+    unsigned int tag, xtag;                  // this launch's tags (kept here, not in registers, across the streaming loops)
+    float4 coef;                             // (mu, scale, shift) of the current item
+    unsigned short order[kPairMaxN];
+    int next_of[kPairMaxN];
+};
+
+// item id -> (channel, sample, piece); recomputed where needed instead of being kept in registers across the streaming loops
+struct PairItem { int c, n, p; };
+__device__ __forceinline__ PairItem pair_item(const PairArgs& a, const unsigned short* order, long long id) {
+    PairItem it;
+    const int per_channel = a.N * a.pieces;
+    it.c = (int)(id / per_channel);
+    const int r0 = (int)(id - (long long)it.c * per_channel);
+    const int k = r0 / a.pieces;
+    it.p = r0 - k * a.pieces;
+    it.n = a.use_order ? (int)order[k] : k;
+    return it;
+}
+
+// Everything between the two passes of a piece, run by warp 0 and kept out of line (its register needs -- the rows of a channel
+// on the first forward -- must not spill into the streaming loops).  `tag` numbers the launches on this workspace (piece
+// words), `xtag` the exchanges on the plane-word table (single GPU: the same number; multi GPU: the peers' shared epoch).
 template <int VEC>
-__device__ __noinline__ void pair_resolve(const PairArgs& a, Moments m, float K, int c, int n, int p, unsigned int tag, uint2* ll_mine,
-                                          size_t ll_words, float* coef, long long* next_id) {
+__device__ __noinline__ void pair_resolve(const PairArgs& a, Moments m, float K, int c, int n, int p, unsigned int tag, unsigned int xtag,
+                                          float4* coef) {
     const int lane = threadIdx.x & 31;
     const int P = a.pieces;
     const bool multi = a.pt.world > 1;
     const bool mix = a.flags & 1, no_noise = a.flags & 2, compute_std = a.flags & 4;
     const float inv_m1 = 1.0f / (float)(a.M - 1);
     const int lo = a.row_offset, hi = a.row_offset + a.N, NG = a.n_global;
-    const int64_t plane = (int64_t)n * a.C + c;
-                const int row = lo + n;
-                const int prow = mix ? (int)a.perm[row] : row;
-                const float lm = mix ? a.lmda[n] : 0.f;
-                float gn = 0.f, bn = 0.f, gs = 0.f, bs = 0.f;
-                if (!no_noise) {
-                    gn = a.gamma_noise[plane]; bn = a.beta_noise[plane];
-                    if (!compute_std) { gs = a.gamma_std[c]; bs = a.beta_std[c]; }
-                }
-                if (P > 1) {
-                    uint2* mine = a.piece_ll + ((size_t)plane * P + p) * 2;
-                    if (lane == 0) { st_ll_dev(mine, m.mean, tag); st_ll_dev(mine + 1, m.m2, tag); }
-                    float pm = m.mean, pq = m.m2;
-                    if (lane < P && lane != p) {
-                        const uint2* w = a.piece_ll + ((size_t)plane * P + lane) * 2;
-                        pair_poll(w, w + 1, tag, false, a.error, pm, pq);
-                    }
-                    __syncwarp();
-                    Moments tot{0.f, 0.f, 0.f};
-                    for (int l = 0; l < P; ++l) {
-                        const float lmean = __shfl_sync(0xffffffffu, pm, l), lm2 = __shfl_sync(0xffffffffu, pq, l);
-                        const int cnt = (min(a.nvec, (l + 1) * a.piece_vecs) - l * a.piece_vecs) * VEC;
-                        tot = merge(tot, Moments{(float)cnt, lmean, lm2});
-                    }
-                    m = tot;
-                }
-                const float mean = K + m.mean;
-                const float sg = sqrtf(m.m2 * inv_m1 + a.eps);
-                if (p == 0) {
-                    uint2* w = ll_mine + ((size_t)row * 2) * a.C + c;
-                    if (multi) {
-                        if (lane == 0) { st_ll(w, mean, tag); st_ll(w + a.C, sg, tag); }
-                        for (int r = lane; r < a.pt.world; r += 32) {
-                            if (r == a.pt.rank) continue;
-                            uint2* dst = reinterpret_cast<uint2*>(a.pt.peers[r]) + (tag & 1u) * ll_words + ((size_t)row * 2) * a.C + c;
-                            st_ll(dst, mean, tag);
-                            st_ll(dst + a.C, sg, tag);
-                        }
-                    } else if (lane == 0) {
-                        st_ll_dev(w, mean, tag);
-                        st_ll_dev(w + a.C, sg, tag);
-                    }
-                    if (lane == 0) {
-                        a.mu[(int64_t)row * a.ld + c] = mean;
-                        a.sig[(int64_t)row * a.ld + c] = sg;
-                    }
-                }
-                if (compute_std) {
-                    // first forward (maxstyle.py:165-168): the whole channel; lane l keeps rows l, l+32, ... in registers
-                    float rm[kPairStdRows], rs[kPairStdRows];
-    #pragma unroll
-                    for (int i = 0; i < kPairStdRows; ++i) {
-                        const int r = lane + 32 * i;
-                        rm[i] = 0.f; rs[i] = 0.f;
-                        if (r < NG) {
-                            if (r == row) { rm[i] = mean; rs[i] = sg; }
-                            else {
-                                const bool remote = r < lo || r >= hi;
-                                const uint2* w = ll_mine + ((size_t)r * 2) * a.C + c;
-                                pair_poll(w, w + a.C, tag, remote, a.error, rm[i], rs[i]);
-                                if (remote && p == 0) { a.mu[(int64_t)r * a.ld + c] = rm[i]; a.sig[(int64_t)r * a.ld + c] = rs[i]; }
-                            }
-                        }
-                    }
-                    float s_sig = 0.f, s_mu = 0.f;
-    #pragma unroll
-                    for (int i = 0; i < kPairStdRows; ++i) { s_sig += rs[i]; s_mu += rm[i]; }      // rows >= NG hold zeros
-                    s_sig = warp_sum(s_sig);
-                    s_mu = warp_sum(s_mu);
-                    const float mean_sig = s_sig / (float)NG, mean_mu = s_mu / (float)NG;
-                    float q_sig = 0.f, q_mu = 0.f;
-    #pragma unroll
-                    for (int i = 0; i < kPairStdRows; ++i) {
-                        if (lane + 32 * i < NG) {
-                            const float ds = rs[i] - mean_sig, dm = rm[i] - mean_mu;
-                            q_sig = fmaf(ds, ds, q_sig);
-                            q_mu = fmaf(dm, dm, q_mu);
-                        }
-                    }
-                    q_sig = warp_sum(q_sig);
-                    q_mu = warp_sum(q_mu);
-                    gs = sqrtf(q_sig / (float)(NG - 1));
-                    bs = sqrtf(q_mu / (float)(NG - 1));
-                    if (lane == 0 && n == 0 && p == 0 && a.gamma_std != nullptr) { a.gamma_std[c] = gs; a.beta_std[c] = bs; }
-                }
-                if (lane == 0) {
-                    float mu_p = mean, sg_p = sg;
-                    if (prow != row) {
-                        const bool remote = prow < lo || prow >= hi;
-                        const uint2* w = ll_mine + ((size_t)prow * 2) * a.C + c;
-                        pair_poll(w, w + a.C, tag, remote, a.error, mu_p, sg_p);
-                        if (remote && p == 0) {                      // the backward reads the partner's row from the local table
-                            a.mu[(int64_t)prow * a.ld + c] = mu_p;
-                            a.sig[(int64_t)prow * a.ld + c] = sg_p;
-                        }
-                    }
-                    float sc, shf;
-                    style_coeffs(sg, mean, sg_p, mu_p, mix, no_noise, lm, gn, bn, gs, bs, sc, shf, !(a.flags & 8));
-                    if (p == 0) { a.scale[plane] = sc; a.shift[plane] = shf; }
-                    coef[0] = mean; coef[1] = sc; coef[2] = shf;
-                    // the wait is over: only now may this CTA hold the ticket of another item (its latency hides under pass 2)
-                    *next_id = (long long)atomicAdd(a.queue, 1ull);
-                }
-}
-
-struct PairShared {
-    Scratch scratch;
-    long long next_id;
-    float coef[4];                           // mu, scale, shift
-    unsigned short order[kPairMaxN];
-    int next_of[kPairMaxN];
-};
-
-template <typename T, int VEC, int VPT>
-__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
-fwd_pair_kernel(const T* __restrict__ x, T* __restrict__ y, PairArgs a) {
-    __shared__ PairShared sh;
-    constexpr int G = kThreads;
-    constexpr int kTail = VPT > 1 ? VPT / 2 : 1;     // loads in flight per thread in the ragged end of a piece
-    const int t = threadIdx.x, lane = t & 31;
-    const int P = a.pieces;
-    const uint64_t pol1 = make_policy(a.pol_first), pol2 = make_policy(a.pol_second), pol_out = make_policy(a.pol_out);
-    const unsigned int tag = *(volatile unsigned int*)a.epoch + 1u;      // advanced by the last CTA out, after every CTA has read it
-    const bool multi = a.pt.world > 1;
-    const int lo = a.row_offset, NG = a.n_global;
-    uint2* ll_mine = a.ll;
+    uint2* ll = a.ll;
     size_t ll_words = 0;
     if (multi) {
         ll_words = (size_t)NG * 2 * a.C;
-        ll_mine = reinterpret_cast<uint2*>(a.pt.peers[a.pt.rank]) + (tag & 1u) * ll_words;
+        ll = reinterpret_cast<uint2*>(a.pt.peers[a.pt.rank]) + (xtag & 1u) * ll_words;
     }
-    if (a.use_order) {
-        // samples in cycle order of perm: n0, perm[n0], perm[perm[n0]], ... -- the plane an item waits for is the next in order
-        for (int i = t; i < a.N; i += G) sh.next_of[i] = (int)a.perm[lo + i] - lo;
-        __syncthreads();
-        if (t == 0) {
-            int k = 0;
-            unsigned int seen[kPairMaxN / 32];
+    const int64_t plane = (int64_t)n * a.C + c;
+    const int row = lo + n;
+    // everything that does not depend on other CTAs is requested before the first wait
+    const int prow = mix ? (int)a.perm[row] : row;
+    const float lm = mix ? a.lmda[n] : 0.f;
+    float gn = 0.f, bn = 0.f, gs = 0.f, bs = 0.f;
+    if (!no_noise) {
+        gn = a.gamma_noise[plane]; bn = a.beta_noise[plane];
+        if (!compute_std) { gs = a.gamma_std[c]; bs = a.beta_std[c]; }
+    }
+    if (P > 1) {
+        uint2* mine = a.piece_ll + ((size_t)plane * P + p) * 2;
+        if (lane == 0) { st_ll_dev(mine, m.mean, tag); st_ll_dev(mine + 1, m.m2, tag); }
+        float pm = m.mean, pq = m.m2;
+        if (lane < P && lane != p) {
+            const uint2* w = a.piece_ll + ((size_t)plane * P + lane) * 2;
+            pair_poll(w, w + 1, tag, false, a.error, pm, pq);
+        }
+        __syncwarp();
+        Moments tot{0.f, 0.f, 0.f};
+        for (int l = 0; l < P; ++l) {                                // piece order: the same sum in every owner
+            const float lmean = __shfl_sync(0xffffffffu, pm, l), lm2 = __shfl_sync(0xffffffffu, pq, l);
+            const int cnt = (min(a.nvec, (l + 1) * a.piece_vecs) - l * a.piece_vecs) * VEC;
+            tot = merge(tot, Moments{(float)cnt, lmean, lm2});
+        }
+        m = tot;
+    }
+    const float mean = K + m.mean;
+    const float sg = sqrtf(m.m2 * inv_m1 + a.eps);
+    if (p == 0) {
+        uint2* w = ll + ((size_t)row * 2) * a.C + c;
+        if (multi) {
+            if (lane == 0) { st_ll(w, mean, xtag); st_ll(w + a.C, sg, xtag); }
+            for (int r = lane; r < a.pt.world; r += 32) {
+                if (r == a.pt.rank) continue;
+                uint2* dst = reinterpret_cast<uint2*>(a.pt.peers[r]) + (xtag & 1u) * ll_words + ((size_t)row * 2) * a.C + c;
+                st_ll(dst, mean, xtag);
+                st_ll(dst + a.C, sg, xtag);
+            }
+        } else if (lane == 0) {
+            st_ll_dev(w, mean, xtag);
+            st_ll_dev(w + a.C, sg, xtag);
+        }
+        if (lane == 0) {
+            a.mu[(int64_t)row * a.ld + c] = mean;
+            a.sig[(int64_t)row * a.ld + c] = sg;
+        }
+    }
+    if (compute_std) {
+        // first forward (maxstyle.py:165-168): the whole channel; lane l keeps rows l, l+32, ... in registers
+        float rm[kPairStdRows], rs[kPairStdRows];
 #pragma unroll
-            for (int w = 0; w < kPairMaxN / 32; ++w) seen[w] = 0u;
-            for (int s0 = 0; s0 < a.N; ++s0) {
-                int n = s0;
-                while (!((seen[n >> 5] >> (n & 31)) & 1u)) {
-                    seen[n >> 5] |= 1u << (n & 31);
-                    sh.order[k++] = (unsigned short)n;
-                    n = sh.next_of[n];
+        for (int i = 0; i < kPairStdRows; ++i) {
+            const int r = lane + 32 * i;
+            rm[i] = 0.f; rs[i] = 0.f;
+            if (r < NG) {
+                if (r == row) { rm[i] = mean; rs[i] = sg; }
+                else {
+                    const bool remote = r < lo || r >= hi;
+                    const uint2* w = ll + ((size_t)r * 2) * a.C + c;
+                    pair_poll(w, w + a.C, xtag, remote, a.error, rm[i], rs[i]);
+                    if (remote && p == 0) { a.mu[(int64_t)r * a.ld + c] = rm[i]; a.sig[(int64_t)r * a.ld + c] = rs[i]; }
                 }
             }
         }
-    }
-    if (t == 0) sh.next_id = (long long)atomicAdd(a.queue, 1ull);
-    if (multi && tag > 1u && t < 32) {
-        // Flow control for the two-parity inboxes: this launch overwrites the words of launch tag-2.  A peer that has published
-        // anything in launch tag-1 has finished launch tag-2: wait for one word of launch tag-1 from each peer (its first row,
-        // last channel -- every exchange kernel publishes it) before the first push.
-        const uint2* prev_inbox = reinterpret_cast<const uint2*>(a.pt.peers[a.pt.rank]) + ((tag - 1u) & 1u) * ll_words;
-        for (int r = lane; r < a.pt.world; r += 32) {
-            if (r == a.pt.rank) continue;
-            const uint2* src = prev_inbox + ((size_t)(r * a.N) * 2) * a.C + (a.C - 1);
-            const long long t0 = clock64();
-            for (;;) {
-                unsigned int bits, got;
-                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(bits), "=r"(got) : "l"(src) : "memory");
-                if ((int)(got - (tag - 1u)) >= 0) break;
-                __nanosleep(100);
-                if (clock64() - t0 > kPairSpinPeer) pair_fail(a.error);
+        float s_sig = 0.f, s_mu = 0.f;
+#pragma unroll
+        for (int i = 0; i < kPairStdRows; ++i) { s_sig += rs[i]; s_mu += rm[i]; }      // rows >= NG hold zeros
+        s_sig = warp_sum(s_sig);
+        s_mu = warp_sum(s_mu);
+        const float mean_sig = s_sig / (float)NG, mean_mu = s_mu / (float)NG;
+        float q_sig = 0.f, q_mu = 0.f;
+#pragma unroll
+        for (int i = 0; i < kPairStdRows; ++i) {
+            if (lane + 32 * i < NG) {
+                const float ds = rs[i] - mean_sig, dm = rm[i] - mean_mu;
+                q_sig = fmaf(ds, ds, q_sig);
+                q_mu = fmaf(dm, dm, q_mu);
             }
         }
+        q_sig = warp_sum(q_sig);
+        q_mu = warp_sum(q_mu);
+        gs = sqrtf(q_sig / (float)(NG - 1));
+        bs = sqrtf(q_mu / (float)(NG - 1));
+        if (lane == 0 && n == 0 && p == 0 && a.gamma_std != nullptr) { a.gamma_std[c] = gs; a.beta_std[c] = bs; }
     }
-    __syncthreads();
-    long long id = sh.next_id;
-    const int per_channel = a.N * P;
-    while (id < a.total_items) {
-        const int c = (int)(id / per_channel);
-        const int r0 = (int)(id - (long long)c * per_channel);
-        const int k = r0 / P, p = r0 - k * P;
-        const int n = a.use_order ? (int)sh.order[k] : k;
-        const int64_t plane = (int64_t)n * a.C + c;
-        Piece pc;
-        pc.plane = plane;
-        pc.v0 = p * a.piece_vecs;
-        pc.v1 = min(a.nvec, pc.v0 + a.piece_vecs);
-        const Batches<G, VPT> bt(pc, false);
-        const T* base = x + plane * a.M;
-        // ---------------- pass 1: moments of the piece (the arithmetic of stats_nchw_kernel) ----------------
-        const float K = to_f32<T>(__ldg(base));
-        Moments acc{0.f, 0.f, 0.f};
-        for (int b = 0; b < bt.full; ++b) {
-            const T* ptr = base + (int64_t)(bt.begin(b) + t) * VEC;
-            float val[VPT][VEC];
+    if (lane == 0) {
+        float mu_p = mean, sg_p = sg;
+        if (prow != row) {
+            const bool remote = prow < lo || prow >= hi;
+            const uint2* w = ll + ((size_t)prow * 2) * a.C + c;
+            pair_poll(w, w + a.C, xtag, remote, a.error, mu_p, sg_p);
+            if (remote && p == 0) {                      // the backward reads the partner's row from the local table
+                a.mu[(int64_t)prow * a.ld + c] = mu_p;
+                a.sig[(int64_t)prow * a.ld + c] = sg_p;
+            }
+        }
+        float sc, shf;
+        style_coeffs(sg, mean, sg_p, mu_p, mix, no_noise, lm, gn, bn, gs, bs, sc, shf, !(a.flags & 8));
+        if (p == 0) { a.scale[plane] = sc; a.shift[plane] = shf; }
+        *coef = make_float4(mean, sc, shf, 0.f);
+    }
+}
+
+// ---- the two streaming passes over a piece [v0, v1) of a plane (inlined: ptxas 12.9 crashes on these loops in a
+// non-inlined function); G threads take part ---------------------------------------------------------------------------
+template <typename T, int VEC, int VPT, int G>
+__device__ __forceinline__ Moments pair_pass1(const T* base, int v0, int v1, int pol_kind, int t, float& K_out) {
+    Piece pc;
+    pc.plane = 0; pc.v0 = v0; pc.v1 = v1;
+    const Batches<G, VPT> bt(pc, false);
+    const uint64_t pol = make_policy(pol_kind);
+    const float K = to_f32<T>(__ldg(base));          // the plane's first element: the same shift in every piece
+    Moments acc{0.f, 0.f, 0.f};
+    for (int b = 0; b < bt.full; ++b) {
+        const T* ptr = base + (int64_t)(bt.begin(b) + t) * VEC;
+        float val[VPT][VEC];
 #pragma unroll
-            for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(ptr + (int64_t)j * G * VEC, val[j], pol1);
+        for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(ptr + (int64_t)j * G * VEC, val[j], pol);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { val[j][e] -= K; s += val[j][e]; }
+        Moments bm;
+        bm.n = (float)(VPT * VEC);
+        bm.mean = s * (1.0f / (float)(VPT * VEC));
+        float qq = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { const float d = val[j][e] - bm.mean; qq = fmaf(d, d, qq); }
+        bm.m2 = qq;
+        acc = merge_fast(acc, bm);
+    }
+    if (bt.rem) {
+        const int rhi = bt.ragged_hi();
+        for (int v = bt.ragged_lo() + t; v < rhi; v += G) {      // the ragged end: one vector per thread and trip
+            float val[VEC];
+            Vec<T, VEC>::load(base + (int64_t)v * VEC, val, pol);
             float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < VPT; ++j)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) { val[j][e] -= K; s += val[j][e]; }
+            for (int e = 0; e < VEC; ++e) { val[e] -= K; s += val[e]; }
             Moments bm;
-            bm.n = (float)(VPT * VEC);
-            bm.mean = s * (1.0f / (float)(VPT * VEC));
+            bm.n = (float)VEC;
+            bm.mean = s * (1.0f / (float)VEC);
             float qq = 0.f;
 #pragma unroll
-            for (int j = 0; j < VPT; ++j)
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) { const float d = val[j][e] - bm.mean; qq = fmaf(d, d, qq); }
+            for (int e = 0; e < VEC; ++e) { const float d = val[e] - bm.mean; qq = fmaf(d, d, qq); }
             bm.m2 = qq;
             acc = merge_fast(acc, bm);
         }
-        if (bt.rem) {
-            // the ragged end of the piece (< G*VPT vectors) as ONE predicated round: all its loads are in flight together
-            const int rhi = bt.ragged_hi();
-            for (int rlo = bt.ragged_lo() + t; rlo < rhi; rlo += kTail * G) {
-            float val[kTail][VEC];
+    }
+    K_out = K;
+    return acc;
+}
+
+template <typename T, int VEC, int VPT, int G>
+__device__ __forceinline__ void pair_pass2(const T* base, T* dst, int v0, int v1, float mu0, float sc, float shf, int pol_in_kind,
+                                           int pol_out_kind, int t) {
+    Piece pc;
+    pc.plane = 0; pc.v0 = v0; pc.v1 = v1;
+    const Batches<G, VPT> bt(pc, false);
+    const uint64_t pol_in = make_policy(pol_in_kind), pol_out = make_policy(pol_out_kind);
+    for (int b = 0; b < bt.full; ++b) {
+        const int64_t o = (int64_t)(bt.begin(b) + t) * VEC;
+        float val[VPT][VEC];
 #pragma unroll
-            for (int j = 0; j < kTail; ++j)
-                if (rlo + j * G < rhi) Vec<T, VEC>::load(base + (int64_t)(rlo + j * G) * VEC, val[j], pol1);
+        for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(base + o + (int64_t)j * G * VEC, val[j], pol_in);
 #pragma unroll
-            for (int j = 0; j < kTail; ++j) {
-                if (rlo + j * G < rhi) {                     // each vector is its own mini-batch
-                    float s = 0.f;
+        for (int j = 0; j < VPT; ++j) {
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) { val[j][e] -= K; s += val[j][e]; }
-                    Moments bm;
-                    bm.n = (float)VEC;
-                    bm.mean = s * (1.0f / (float)VEC);
-                    float qq = 0.f;
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) { const float d = val[j][e] - bm.mean; qq = fmaf(d, d, qq); }
-                    bm.m2 = qq;
-                    acc = merge_fast(acc, bm);
-                }
-            }
-            }
+            for (int e = 0; e < VEC; ++e) val[j][e] = fmaf(val[j][e] - mu0, sc, shf);
+            Vec<T, VEC>::store(dst + o + (int64_t)j * G * VEC, val[j], pol_out);
         }
-        Moments m = group_merge<G>(acc, sh.scratch);             // valid in every thread
-        // ---------------- publish / partner: warp 0 ----------------
-        if (t < 32) pair_resolve<VEC>(a, m, K, c, n, p, tag, ll_mine, ll_words, sh.coef, &sh.next_id);
-        __syncthreads();
-        const float mu0 = sh.coef[0], sc = sh.coef[1], shf = sh.coef[2];
-        const long long next = sh.next_id;
-        // ---------------- pass 2: the same piece again (L2), y out ----------------
-        T* dst = y + plane * a.M;
-        for (int b = 0; b < bt.full; ++b) {
-            const int64_t o = (int64_t)(bt.begin(b) + t) * VEC;
-            float val[VPT][VEC];
+    }
+    if (bt.rem) {
+        const int rhi = bt.ragged_hi();
+        for (int v = bt.ragged_lo() + t; v < rhi; v += G) {
+            float val[VEC];
+            Vec<T, VEC>::load(base + (int64_t)v * VEC, val, pol_in);
 #pragma unroll
-            for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(base + o + (int64_t)j * G * VEC, val[j], pol2);
-#pragma unroll
-            for (int j = 0; j < VPT; ++j) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) val[j][e] = fmaf(val[j][e] - mu0, sc, shf);
-                Vec<T, VEC>::store(dst + o + (int64_t)j * G * VEC, val[j], pol_out);
-            }
+            for (int e = 0; e < VEC; ++e) val[e] = fmaf(val[e] - mu0, sc, shf);
+            Vec<T, VEC>::store(dst + (int64_t)v * VEC, val, pol_out);
         }
-        if (bt.rem) {
-            const int rhi = bt.ragged_hi();
-            for (int rlo = bt.ragged_lo() + t; rlo < rhi; rlo += kTail * G) {
-                float val[kTail][VEC];
+    }
+}
+
+template <typename T, int VEC, int VPT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+fwd_pair_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_constant__ PairArgs a) {
+    __shared__ PairShared sh;
+    constexpr int G = kThreads;
+    const int t = threadIdx.x;
+    {
+        const unsigned int wtag = *(volatile unsigned int*)a.wepoch + 1u;      // advanced by the last CTA out, after every CTA has read them
+        const unsigned int xtag = a.pt.world > 1 ? *(volatile unsigned int*)a.epoch + 1u : wtag;
+        const int lo = a.row_offset;
+        if (a.use_order) {
+            for (int i = t; i < a.N; i += G) sh.next_of[i] = (int)a.perm[lo + i] - lo;
+            __syncthreads();
+            if (t == 0) {
+                int k = 0;
+                unsigned int seen[kPairMaxN / 32];
 #pragma unroll
-                for (int j = 0; j < kTail; ++j)
-                    if (rlo + j * G < rhi) Vec<T, VEC>::load(base + (int64_t)(rlo + j * G) * VEC, val[j], pol2);
-#pragma unroll
-                for (int j = 0; j < kTail; ++j) {
-                    if (rlo + j * G < rhi) {
-#pragma unroll
-                        for (int e = 0; e < VEC; ++e) val[j][e] = fmaf(val[j][e] - mu0, sc, shf);
-                        Vec<T, VEC>::store(dst + (int64_t)(rlo + j * G) * VEC, val[j], pol_out);
+                for (int w = 0; w < kPairMaxN / 32; ++w) seen[w] = 0u;
+                for (int s0 = 0; s0 < a.N; ++s0) {
+                    int n = s0;
+                    while (!((seen[n >> 5] >> (n & 31)) & 1u)) {
+                        seen[n >> 5] |= 1u << (n & 31);
+                        sh.order[k++] = (unsigned short)n;
+                        n = sh.next_of[n];
                     }
                 }
             }
         }
-        id = next;                             // coef / next_id are rewritten only after the next item's block reduction (two barriers)
+        if (t == 0) { sh.next_id = (long long)atomicAdd(a.queue, 1ull); sh.tag = wtag; sh.xtag = xtag; }
+        if (a.pt.world > 1 && xtag > 1u && t < 32) {
+            // Flow control for the two-parity inboxes: this launch overwrites the words of launch xtag-2.  A peer that has published
+            // anything in launch xtag-1 has finished launch xtag-2: wait for one word of launch xtag-1 from each peer (its first row,
+            // last channel -- every exchange kernel publishes it) before the first push.
+            const size_t ll_words = (size_t)a.n_global * 2 * a.C;
+            const uint2* prev_inbox = reinterpret_cast<const uint2*>(a.pt.peers[a.pt.rank]) + ((xtag - 1u) & 1u) * ll_words;
+            for (int r = t; r < a.pt.world; r += 32) {
+                if (r == a.pt.rank) continue;
+                const uint2* src = prev_inbox + ((size_t)(r * a.N) * 2) * a.C + (a.C - 1);
+                const long long t0 = clock64();
+                for (;;) {
+                    unsigned int bits, got;
+                    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(bits), "=r"(got) : "l"(src) : "memory");
+                    if ((int)(got - (xtag - 1u)) >= 0) break;
+                    __nanosleep(100);
+                    if (clock64() - t0 > kPairSpinPeer) pair_fail(a.error);
+                }
+            }
+        }
+        __syncthreads();
     }
-    // ---- the last CTA out closes the launch: ticket counter back to zero, launch counter advanced ----
+    long long id = sh.next_id;
+    while (id < a.total_items) {
+        const PairItem it = pair_item(a, sh.order, id);
+        const int64_t plane = (int64_t)it.n * a.C + it.c;
+        const int v0 = it.p * a.piece_vecs, v1 = min(a.nvec, v0 + a.piece_vecs);
+        float K;
+        const Moments acc = pair_pass1<T, VEC, VPT, G>(x + plane * a.M, v0, v1, a.pol_first, t, K);
+        const Moments m = group_merge<G>(acc, sh.scratch);             // valid in every thread
+        if (t < 32) {
+            pair_resolve<VEC>(a, m, K, it.c, it.n, it.p, sh.tag, sh.xtag, &sh.coef);
+            // the wait is over: only now may this CTA hold the ticket of another item (its latency hides under pass 2)
+            if (t == 0) sh.next_id = (long long)atomicAdd(a.queue, 1ull);
+        }
+        __syncthreads();
+        const float4 cf = sh.coef;
+        id = sh.next_id;                       // coef / next_id are rewritten only after the next item's block reduction (two barriers)
+        pair_pass2<T, VEC, VPT, G>(x + plane * a.M, y + plane * a.M, v0, v1, cf.x, cf.y, cf.z, a.pol_second, a.pol_out, t);
+    }
     if (t == 0) {
         __threadfence();
         if (atomicAdd(a.done, 1u) == gridDim.x - 1u) {
             *a.done = 0u;
             *a.queue = 0ull;
-            *a.epoch = tag;
+            *a.wepoch = sh.tag;
+            if (a.pt.world > 1) *a.epoch = sh.xtag;
             __threadfence();
         }
     }

@@ -325,15 +325,17 @@ inline PairPlan make_pair_plan(int64_t M, int dtype, int align, int force_pieces
     p.vpt = vpt_one_tensor(p.vec);
     int64_t P = force_pieces;
     if (P <= 0) {
-        // A piece costs ceil(vectors / round) latency rounds of 256 x vpt vectors plus ~1.5 rounds of publish / partner gap, and
-        // must stay small enough for 592 of them to live in L2 between their two passes: the fewest pieces of at most
+        // A piece of `len` vectors costs, per pass, len / round full rounds (256 threads x vpt loads in flight each) plus one
+        // trip per 256 vectors of its ragged end, and ~1.5 rounds of publish / partner gap; 592 pieces must stay in L2 between
+        // their passes (measured: 16 % of the second reads miss at 59 MB alive, 68 % at 89 MB): the fewest pieces of at most
         // `piece_bytes` (~112 KB), then the cheapest of the next few counts.
         const int64_t round = (int64_t)kThreadsPerBlock * p.vpt;
         const int64_t first = ceil_div(pb, piece_bytes);
         double best = 0.0;
-        for (int64_t cand = first; cand <= first + 3 && cand <= kPairMaxPieces; ++cand) {
+        for (int64_t cand = first; cand <= first + 8 && cand <= kPairMaxPieces; ++cand) {
             const int64_t pv = ceil_div(nvec, cand);
-            const double cost = (double)ceil_div(nvec, pv) * ((double)ceil_div(pv, round) + 1.5);
+            const double trips = (double)(pv / round) + (double)ceil_div(pv % round, kThreadsPerBlock);
+            const double cost = (double)ceil_div(nvec, pv) * (trips + 1.5);
             if (P <= 0 || cost < best) { P = cand; best = cost; }
         }
     }
@@ -350,12 +352,13 @@ inline PairPlan make_pair_plan(int64_t M, int dtype, int align, int force_pieces
 //                            [fused forward: error flag + queue + done 256 B][arrived | ready: 2 x C x u32][item partials]
 //                            [resident forward: plane ready flags, planes x u32]
 //                            [cluster forward: {value, tag} words, planes x 2 x 8 B][piece words, planes x max pieces x 2 x 8 B]
-//                            (its launch counter: u32 @24 of the error block)
+//                            [paired forward: {tag, pieces published} per plane, planes x u64]
+//                            (their launch counter: u32 @24 of the error block)
 // slots_bound covers every plan make_plan() can produce for this shape:
 //   slots = ceil(nvec/per) + 1  with  per >= total/kMaxGrid  =>  slots <= kMaxGrid/planes + 2.
 // NHWC (layout 1): the shared unit is the sample, each CTA publishes C partials for it (make_plan_nhwc).
 struct Workspace {
-    size_t plane_tickets, sample_tickets, done_counter, partials, res_error, res_flags, res_partials, plane_ready, cl_words, cl_pieces, total;
+    size_t plane_tickets, sample_tickets, done_counter, partials, res_error, res_flags, res_partials, plane_ready, cl_words, cl_pieces, pair_count, total;
     int slots_bound, max_pieces;
 };
 
@@ -398,6 +401,7 @@ inline Workspace workspace_layout(int N, int C, int64_t M, int dtype, int layout
         w.cl_pieces = off; off = align_up(off + (size_t)planes * mp * 2 * 8, 256);
         w.max_pieces = mp;
     }
+    w.pair_count = off; off = align_up(off + (size_t)planes * 8, 256);
     w.total = off;
     return w;
 }

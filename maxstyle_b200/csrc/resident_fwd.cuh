@@ -81,7 +81,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > kFusedSpinLimit) { *error = 1; return false; }
+        if (clock64() - t0 > kFusedSpinLimit) wait_timed_out(error);
     }
     return true;
 }
@@ -165,7 +165,7 @@ fwd_resident_kernel(const T* __restrict__ x, T* __restrict__ y, ResidentArgs a) 
         // =============================== consumer warps ===============================
         const int warp = t >> 5, lane = t & 31;
         const uint64_t pol_out = make_policy(a.io_policy);
-        const bool mix = a.flags & 1, no_noise = a.flags & 2, need_std = (a.flags & 4) && !no_noise;
+        const bool mix = a.flags & 1, no_noise = a.flags & 2, need_std = (a.flags & 4) && a.gamma_std != nullptr;     // the reference fills the cache whatever no_noise says (:165-168)
         const float inv_m1 = 1.0f / (float)(a.M - 1);
         const int N = a.N, C = a.C;
         for (int p = 0;; ++p) {
@@ -250,7 +250,7 @@ fwd_resident_kernel(const T* __restrict__ x, T* __restrict__ y, ResidentArgs a) 
                         const int64_t q = (int64_t)r * C + c;
                         while (ld_acquire_u32(&a.ready[q]) == 0u) {
                             __nanosleep(64);
-                            if (clock64() - t0 > kFusedSpinLimit) { *a.error = 1; break; }
+                            if (clock64() - t0 > kFusedSpinLimit) wait_timed_out(a.error);
                         }
                         sh.fin_mu[r] = __ldcg(a.mu + q);
                         sh.fin_sig[r] = __ldcg(a.sig + q);
@@ -282,7 +282,7 @@ fwd_resident_kernel(const T* __restrict__ x, T* __restrict__ y, ResidentArgs a) 
                         const long long t0 = clock64();
                         while (ld_acquire_u32(&a.ready[q]) == 0u) {
                             __nanosleep(32);
-                            if (clock64() - t0 > kFusedSpinLimit) { *a.error = 1; break; }
+                            if (clock64() - t0 > kFusedSpinLimit) wait_timed_out(a.error);
                         }
                         sg_p = __ldcg(a.sig + q);
                         mu_p = __ldcg(a.mu + q);

@@ -125,7 +125,7 @@ fwd_ring_kernel(const T* __restrict__ x, T* __restrict__ y, FusedArgs a, RingGeo
                         const long long t0 = clock64();
                         while (ld_acquire_u32(&a.ready[it.c]) == 0u) {
                             __nanosleep(64);
-                            if (clock64() - t0 > kFusedSpinLimit) { *a.error = 1; break; }
+                            if (clock64() - t0 > kFusedSpinLimit) wait_timed_out(a.error);
                         }
                     }
                     named_sync(kBarRed, TC);

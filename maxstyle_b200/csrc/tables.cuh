@@ -143,7 +143,7 @@ tables_p2p_kernel(PeerTables pt, float* __restrict__ mu_all, float* __restrict__
         float m = 0.f, sg = 0.f;
         const long long t0 = clock64();
         while (!(ld_ll(src, epoch, m) & ld_ll(src + C, epoch, sg))) {
-            if (clock64() - t0 > 4000000000LL) { *pt.error = 1; break; }
+            if (clock64() - t0 > 40000000000LL) wait_timed_out(pt.error);      // ~20 s: another rank may be late, not dead
         }
         mu_all[row * ld + c] = m;
         sig_all[row * ld + c] = sg;
@@ -181,7 +181,7 @@ rank_barrier_kernel(PeerTables pt, size_t barrier_offset_words, unsigned int* ba
         float who;
         const long long t0 = clock64();
         while (!ld_ll(src, epoch, who)) {
-            if (clock64() - t0 > 4000000000LL) { *pt.error = 1; break; }
+            if (clock64() - t0 > 40000000000LL) wait_timed_out(pt.error);      // ~20 s: another rank may be late, not dead
         }
     }
     __syncwarp();

@@ -106,8 +106,10 @@ class GlobalBatchMaxStyle(MaxStyle):
 
     `batch_size` is the LOCAL batch (what this rank's feature map has); the random state is drawn
     for the global batch exactly like the reference would on the concatenated batch -- seed every
-    rank identically (torch.manual_seed(s)) to reproduce the single-device reference bit for bit;
-    perm and rand_p are broadcast from rank 0 regardless -- and this rank keeps its rows.
+    rank identically (torch.manual_seed(s)) to reproduce the single-device reference bit for bit.
+    With different seeds per rank the layer is still consistent: perm and rand_p are rank 0's on
+    every rank (agreed before anything is allocated from them), each rank's parameter rows come
+    from its own draw -- and this rank keeps its rows.
     """
 
     def __init__(self, batch_size, num_feature, p=0.5, mix_style=True, no_noise=False, mix_learnable=True,
@@ -121,6 +123,14 @@ class GlobalBatchMaxStyle(MaxStyle):
                          mix_learnable=mix_learnable, noise_learnable=noise_learnable, always_use_beta=always_use_beta,
                          alpha=alpha, eps=eps, use_gpu=use_gpu, debug=debug)
 
+    def _agree_on_draw(self):
+        """Every rank takes rank 0's permutation and rank 0's activity draw -- BEFORE the parameters are allocated from
+        rand_p (ranks seeded differently would otherwise disagree on whether the layer is active, and a rank whose own
+        draw was inactive would run an active forward with zero, non-learnable parameters)."""
+        dev = self.device if self.use_gpu else None
+        self.perm = self._exchange.agree(self.perm, dev)
+        self.rand_p = self._exchange.agree(self.rand_p, dev)
+
     def init_parameters(self):
         n_loc, n_glob, off = self.local_batch_size, self.global_batch_size, self.row_offset
         self.batch_size = n_glob                       # draw the reference's state for the global batch ...
@@ -128,9 +138,6 @@ class GlobalBatchMaxStyle(MaxStyle):
             super().init_parameters()
         finally:
             self.batch_size = n_loc
-        dev = self.device if self.use_gpu else None
-        self.perm = self._exchange.agree(self.perm, dev)
-        self.rand_p = self._exchange.agree(self.rand_p, dev)
         self._perm_dev = None
 
         def local_rows(t):                             # ... and keep this rank's rows

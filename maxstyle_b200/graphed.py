@@ -31,10 +31,9 @@ class GraphedLayerStep:
             exchange + tables kernel over NVLink peer memory (maxstyle_tables_p2p; collective construction); "nccl":
             all_gather_into_tensor then the table kernel; "auto": p2p when symmetric memory can be set up on every rank,
             else nccl (`self.exchange` says which).
-        one_kernel (with the p2p exchange): run the whole forward as the one-kernel L2-window forward with the exchange in
-            its channel finaliser (maxstyle_fwd_p2p) when the shape qualifies; False: statistics -> exchange + tables -> apply.
-            Default: on at 2 ranks, off beyond -- with more ranks the skew between them outgrows the 32 MB window that hides
-            the exchange and the apply items stall (profiles/r01_multi.txt).
+        one_kernel (with the p2p exchange): run the whole forward as ONE kernel that also exchanges the (mu | sig) rows over peer
+            memory (maxstyle_fwd_p2p: the paired forward pushes a plane's statistics into every peer's inbox the moment it has
+            them) when the shape qualifies; False: statistics -> exchange + tables -> apply.  Default: on.
     Attributes: `y`, `dx` (static outputs), `grads` = (d_gamma, d_beta, d_lmda) when the layer has no fused step or it
     keeps gradients, `kernels_per_step` (for launch accounting).
     """
@@ -72,8 +71,8 @@ class GraphedLayerStep:
         self.start_barrier = os.environ.get("MAXSTYLE_START_BARRIER", "0") == "1"
         if one_kernel is None and os.environ.get("MAXSTYLE_ONE_KERNEL") in ("0", "1"):
             one_kernel = os.environ["MAXSTYLE_ONE_KERNEL"] == "1"      # experiments
-        if one_kernel is None:                                   # measured: 268 vs 275.5 us/step at 2 ranks, 307 vs 277 at 4
-            one_kernel = self.distributed and layer._exchange.world <= 2
+        if one_kernel is None:                                   # the library declines (and the three-call path runs) where it does not pay
+            one_kernel = self.distributed
         self.one_kernel = None if one_kernel else False          # None: ask maxstyle_fwd_p2p on the first call
         if self.distributed:
             self.table = layer._exchange.allocate(n, c, dev)

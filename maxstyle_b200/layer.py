@@ -77,6 +77,10 @@ class MaxStyle(nn.Module):
             perm = torch.randperm(n)
         return perm
 
+    def _agree_on_draw(self):
+        """Hook between the two CPU draws (perm, rand_p) and everything that depends on them.  The multi-GPU layer
+        overrides it to take rank 0's draw on every rank BEFORE parameters are allocated from rand_p."""
+
     def init_parameters(self):
         n, c, dev = self.batch_size, self.num_feature, self.device
         self.perm = self._draw_permutation()
@@ -84,6 +88,7 @@ class MaxStyle(nn.Module):
         if self.debug:
             print("permutation index", self.perm)
         self.rand_p = torch.rand(1)
+        self._agree_on_draw()
         active = bool(self.rand_p < self.p)
 
         def const_table(shape):
@@ -156,9 +161,10 @@ class MaxStyle(nn.Module):
         (construct with p=1.0 storage via StyleLoopExecutor); returns whether the layer is active for this draw."""
         n, c, dev = self.batch_size, self.num_feature, self.device
         self.perm = self._draw_permutation()
+        self.rand_p = torch.rand(1)
+        self._agree_on_draw()
         if self._perm_dev is not None:
             self._perm_dev.copy_(self.perm.to(torch.int64), non_blocking=False)
-        self.rand_p = torch.rand(1)
         active = bool(self.rand_p < self.p)
         if active:
             if self.no_noise:

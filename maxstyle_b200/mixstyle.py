@@ -119,9 +119,12 @@ class MixStyle(nn.Module):
                         perm_a = perm_a[torch.randperm(B // 2)]
                         perm = torch.cat([perm_b, perm_a], 0)
                 self.perm = perm
-                perm_dev = torch.as_tensor(perm).to(device=x.device, dtype=torch.int64)
-                if perm_dev.numel() != B or int(perm_dev.min()) < 0 or int(perm_dev.max()) >= B:
+                perm_t = torch.as_tensor(perm)
+                # range check on the HOST copy only (the reference's perm is a CPU tensor): no device synchronisation on the
+                # forward path, so the call stays graph-capturable; a caller-supplied CUDA perm is taken as it is
+                if perm_t.numel() != B or (not perm_t.is_cuda and B > 0 and (int(perm_t.min()) < 0 or int(perm_t.max()) >= B)):
                     raise IndexError("maxstyle_b200: perm must hold B indices into the batch")
+                perm_dev = perm_t.to(device=x.device, dtype=torch.int64)
                 state = _CallState(L.FLAG_MIX_STYLE | L.FLAG_NO_NOISE | L.FLAG_NO_CLAMP, self.eps, C, perm_dev,
                                    self._workspace_for(F.dense_layout(x)))
                 state.gamma_std = torch.zeros(1, C, 1, 1, device=x.device)        # unused with NO_NOISE; keeps the one-kernel path

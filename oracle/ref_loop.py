@@ -103,9 +103,24 @@ def run_loop(ref, solver, image_v, label_v, layer_cls, *, seed=7, p=1.0, n_iter=
 
 
 def first_iteration_grads(ref, solver, image_v, label_v, layer_cls, *, seed=7, p=1.0, layers=(3, 4, 5),
-                          channel_num=(128, 64, 32, 16, 16, 1), always_use_beta=True):
+                          channel_num=(128, 64, 32, 16, 16, 1), always_use_beta=True, double=False):
     """Gradients of the reference's loop at its first iteration, without the optimiser step: the loop body of model:539-566
-    (decode with the layers, re-encode, segment, -CE, backward) driven through the reference's own methods."""
+    (decode with the layers, re-encode, segment, -CE, backward) driven through the reference's own methods.
+    `double=True` runs networks and layers in float64 (the same weights and the same float32 parameter draws, widened):
+    the yardstick against which float32 runs of the reference layer and of a replacement are both measured."""
+    use_gpu = image_v.is_cuda
+    if double:
+        for m in solver.model.values():
+            m.double()
+        try:
+            return _first_iteration(ref, solver, image_v.double(), label_v, layer_cls, seed, p, layers, channel_num, always_use_beta, True)
+        finally:
+            for m in solver.model.values():
+                m.float()                  # float(double(w)) == w: the float32 weights come back bit for bit
+    return _first_iteration(ref, solver, image_v, label_v, layer_cls, seed, p, layers, channel_num, always_use_beta, False)
+
+
+def _first_iteration(ref, solver, image_v, label_v, layer_cls, seed, p, layers, channel_num, always_use_beta, double):
     use_gpu = image_v.is_cuda
     torch.manual_seed(seed)
     with torch.no_grad():
@@ -118,13 +133,29 @@ def first_iteration_grads(ref, solver, image_v, label_v, layer_cls, *, seed=7, p
             kw["use_gpu"] = False
         mods[str(i)] = layer_cls(n, channel_num[i], **kw)
     md = torch.nn.ModuleDict(mods)
+    if double:
+        md.double()
     for m in solver.model.values():
         ref.basic_operations.set_grad(m, requires_grad=False)
+    captured = {}
+
+    def grab(key):
+        def hook(_mod, inputs, output):
+            captured[key] = [inputs[0].detach().clone(), None]
+            if output.requires_grad:
+                output.register_hook(lambda g: captured[key].__setitem__(1, g.detach().clone()))
+        return hook
+
+    handles = [m.register_forward_hook(grab(k)) for k, m in mods.items()]
     recon = solver.model["image_decoder"].apply_max_style(z_i, decoder_layers_indexes=list(layers), nn_style_augmentor_dict=md)
+    for h_ in handles:
+        h_.remove()
     zi2, zs2 = solver.encode_image(recon, disable_track_bn_stats=True)
     pred = solver.decoder_inference(decoder=solver.model["segmentation_decoder"], latent_code=zs2, eval=False, disable_track_bn_stats=True)
     loss = -ref.custom_loss.basic_loss_fn(pred=pred, target=label_v, loss_type="cross entropy", class_weights=None, use_gpu=use_gpu)
     loss.backward()
     grads = {k: {name: (prm.grad.detach().clone() if prm.grad is not None else None) for name, prm in m.named_parameters()}
              for k, m in mods.items()}
+    for k, m in mods.items():
+        m.captured_io = tuple(captured.get(k, (None, None)))       # (input feature map, upstream gradient) of this layer in the loop
     return recon.detach(), float(loss.detach()), grads, mods

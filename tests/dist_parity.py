@@ -157,6 +157,36 @@ def main():
     for i, nm in enumerate(("y", "dx", "d_gamma", "d_beta", "d_lmda", "gamma_std", "beta_std") if "one" in outs else ()):
         a_, b_ = t2n(outs["one"][i]), t2n(outs["nccl"][i])
         errs[f"one_kernel_vs_nccl_{nm}"] = close(a_, b_, 1e-5 if nm in ("y", "gamma_std", "beta_std") else 1e-4, f"one-kernel vs nccl {nm}")
+    # ---- the path bench.py / SCALE time: per-rank planes of 196 KB (CTA-mode statistics / apply / backward, the one-kernel
+    # paired forward with its peer pushes, maxstyle_tables_p2p at world x 8 rows), every transport, first forward + replays,
+    # against the float64 oracle on the CONCATENATED batch (bench.parity_check: reference semantics, maxstyle.py:157-185 with
+    # perm over the global batch) -- y <= 1e-5, gradients <= 1e-4, batch std <= 1e-5, perm bit-exact.
+    from bench import parity_check
+    seed = 4321
+    nb, cb, hb, wb = 8, 8, 224, 224
+    for transport in ("p2p-one-kernel", "p2p", "nccl"):
+        torch.manual_seed(seed)
+        lay = GlobalBatchMaxStyle(nb, cb, p=1.0)
+        genb = torch.Generator(device=dev).manual_seed(900 + rank)
+        xr = torch.randn(nb, cb, hb, wb, device=dev, generator=genb) * (1.0 + 0.3 * rank) + 0.2 * rank
+        dyr = torch.randn(nb, cb, hb, wb, device=dev, generator=genb)
+        try:
+            gsr = GraphedLayerStep(lay, xr, dyr, exchange=transport.split("-")[0], one_kernel=transport == "p2p-one-kernel")
+        except RuntimeError as e:
+            if "peer-memory exchange requested but not available" not in str(e):
+                raise
+            errs[f"bench_path_{transport}"] = "symmetric memory unavailable on this system: skipped (every rank agrees)"
+            continue
+        if transport == "p2p-one-kernel":
+            assert gsr.one_kernel is True and gsr.kernels_per_step == 2, (gsr.one_kernel, gsr.kernels_per_step)
+        for _ in range(4):
+            gsr.run()
+        par = parity_check(lay, gsr, world, rank, dev, seed)
+        assert par["ok"], f"rank {rank} {transport}: {par}"
+        errs[f"bench_path_{transport}"] = {k: par[k] for k in ("y", "dx", "d_gamma", "d_beta", "d_lmda", "gamma_std", "beta_std")}
+        gsr.close()
+        torch.cuda.synchronize()
+        dist.barrier()
     print(f"[dist_parity] rank {rank}/{world} ok", json.dumps({k: (v if isinstance(v, (float, str)) else {a: f"{b:.1e}" for a, b in v.items()})
                                                                 for k, v in errs.items()}), flush=True)
     sys.stdout.flush()

@@ -14,8 +14,12 @@ with open(os.path.join(GOLDEN, "CE2D_MANIFEST.json")) as _f:
     CASES = json.load(_f)["cases"]
 
 
-def _case(golden, c):
-    g = golden["ce2d"]
+with open(os.path.join(GOLDEN, "CE2D_SOFT_MANIFEST.json")) as _f:
+    SOFT_CASES = json.load(_f)["cases"]
+
+
+def _case(golden, c, name="ce2d"):
+    g = golden[name]
     pre = f"c{c['idx']}_"
     return {k[len(pre):]: v for k, v in g.items() if k.startswith(pre)}
 
@@ -33,10 +37,24 @@ def test_oracle_matches_reference_cross_entropy(golden, c):
     assert np.abs(grad - rec["dlogits"]).max() <= 2e-6 * max(np.abs(rec["dlogits"]).max(), 1e-12) + 1e-9
 
 
+@pytest.mark.parametrize("c", SOFT_CASES, ids=lambda c: f"soft{c['idx']}")
+def test_oracle_matches_reference_soft_target_branch(golden, c):
+    """custom_loss.py:1079-1102 (4-d target: logits, or probabilities with is_gt) -- loss, d/d logits and d/d target."""
+    rec = _case(golden, c, "ce2d_soft")
+    kw = dict(weight=c["weights"], size_average=c["size_average"], mask=rec.get("mask"), is_gt=c["is_gt"])
+    loss = CO.cross_entropy_2d_soft(rec["logits"], rec["target"], **kw)
+    dl, dt = CO.cross_entropy_2d_soft_grad(rec["logits"], rec["target"], dloss=c["dloss"], **kw)
+    assert abs(loss - rec["loss"]) <= 5e-6 * max(abs(rec["loss"]), 1e-6) + 1e-7
+    assert np.abs(dl - rec["dlogits"]).max() <= 5e-6 * max(np.abs(rec["dlogits"]).max(), 1e-12) + 1e-9
+    assert np.abs(dt - rec["dtarget"]).max() <= 5e-6 * max(np.abs(rec["dtarget"]).max(), 1e-12) + 1e-9
+
+
 def test_cross_entropy_error_behaviour_on_cpu():
     from maxstyle_b200.losses import cross_entropy_2D
-    with pytest.raises(NotImplementedError):
-        cross_entropy_2D(torch.randn(2, 3, 4, 4), torch.randn(2, 3, 4, 4))          # soft-target branch not built
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cross_entropy_2D(torch.randn(2, 3, 4, 4), torch.randn(2, 3, 4, 4))          # soft-target branch: CUDA only, like the rest
+    with pytest.raises(RuntimeError, match="does not match"):
+        cross_entropy_2D(torch.randn(2, 3, 4, 4), torch.randn(2, 5, 4, 4))
     with pytest.raises(NotImplementedError):
         cross_entropy_2D(torch.randn(2, 3, 4, 4), torch.zeros(2, 4, dtype=torch.int64))
     with pytest.raises(RuntimeError, match="no CPU path"):
@@ -65,6 +83,42 @@ def test_cuda_cross_entropy_matches_reference(golden, c):
     g64 = CO.cross_entropy_2d_grad(rec["logits"], rec["target"], c["weights"], c["size_average"], rec.get("mask"), dloss=c["dloss"])
     assert abs(losses[0] - l64) <= 1e-5 * max(abs(l64), 1e-6) + 1e-7
     assert np.abs(x.grad.cpu().numpy() - g64).max() <= 1e-4 * max(np.abs(g64).max(), 1e-12) + 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", SOFT_CASES, ids=lambda c: f"soft{c['idx']}")
+def test_cuda_cross_entropy_soft_target_matches_reference(golden, c):
+    from maxstyle_b200.losses import cross_entropy_2D
+    rec = _case(golden, c, "ce2d_soft")
+    mask = None if "mask" not in rec else torch.from_numpy(rec["mask"]).cuda()
+    for target_grad in (True, False):
+        x = torch.from_numpy(rec["logits"]).cuda().requires_grad_(True)
+        t = torch.from_numpy(rec["target"]).cuda().requires_grad_(target_grad)
+        loss = cross_entropy_2D(x, t, weight=c["weights"], size_average=c["size_average"], mask=mask, is_gt=c["is_gt"])
+        (loss * c["dloss"]).backward()
+        assert abs(float(loss) - float(rec["loss"])) <= 1e-5 * max(abs(float(rec["loss"])), 1e-6) + 1e-7
+        assert _rel(x.grad.cpu().numpy(), rec["dlogits"]) < 1e-4
+        if target_grad:
+            assert _rel(t.grad.cpu().numpy(), rec["dtarget"]) < 1e-4
+        else:
+            assert t.grad is None
+
+
+@pytest.mark.gpu
+def test_cuda_cross_entropy_more_classes_than_registers_and_no_grad():
+    """C > 8 takes the two-kernel path; a loss nobody differentiates computes no gradient."""
+    from maxstyle_b200.losses import cross_entropy_2D
+    import torch.nn.functional as TF
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(3, 11, 20, 24, device="cuda", generator=g).requires_grad_(True)
+    t = torch.randint(0, 11, (3, 20, 24), device="cuda", generator=g)
+    loss = cross_entropy_2D(x, t)
+    loss.backward()
+    ref = TF.cross_entropy(x.detach().requires_grad_(True), t)
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    with torch.no_grad():
+        plain = cross_entropy_2D(torch.randn(2, 4, 8, 8, device="cuda"), torch.randint(0, 4, (2, 8, 8), device="cuda"))
+    assert plain.dim() == 0 and not plain.requires_grad
 
 
 @pytest.mark.gpu

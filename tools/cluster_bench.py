@@ -29,7 +29,7 @@ def main():
     FC = L.SWEEP_FORCE_CLUSTER
     variants = [("default", 0), ("two_pass", L.SWEEP_NO_FUSED), ("window", L.SWEEP_NO_RESIDENT | L.SWEEP_NO_RING | L.SWEEP_FORCE_WINDOW),
                 ("resident", L.SWEEP_FORCE_RESIDENT), ("cluster_auto", FC)]
-    for pc in (0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 16, 24, 32):
+    for pc in (0, 1, 2, 3, 4, 5, 6, 7, 8, 11, 12, 16, 24, 32):
         variants.append((f"pair_p{pc}", L.SWEEP_FORCE_PAIR | (pc << L.SWEEP_CLUSTER_PIECES_SHIFT)))
     variants.append(("pair_p0_normal", L.SWEEP_FORCE_PAIR | L.SWEEP_X_STREAM))
     variants.append(("pair_p4_normal", L.SWEEP_FORCE_PAIR | L.SWEEP_X_STREAM | (4 << L.SWEEP_CLUSTER_PIECES_SHIFT)))
