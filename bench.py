@@ -197,6 +197,11 @@ def parity_check(layer, gstep, world, rank, dev, seed):
     from oracle import maxstyle_oracle as O
     n, c, h, w = gstep.x.shape
     f64 = np.float64
+    # After hundreds of Adam(lr=0.1) steps on random gradients lmda has left [0, 1] on most samples, where the clamp's gradient
+    # is zero (the reference's behaviour) -- d_lmda would be checked as 0 == 0.  Put it back inside.
+    with torch.no_grad():
+        gen = torch.Generator().manual_seed(4242 + rank)
+        layer.lmda.copy_((torch.rand(n, generator=gen) * 0.9 + 0.05).view_as(layer.lmda))
     gam = layer.gamma_noise.detach().float().cpu().numpy().reshape(n, c).astype(f64)
     bet = layer.beta_noise.detach().float().cpu().numpy().reshape(n, c).astype(f64)
     lm = layer.lmda.detach().float().cpu().numpy().reshape(n).astype(f64)
@@ -259,6 +264,7 @@ def parity_check(layer, gstep, world, rank, dev, seed):
     vals = t.tolist()
     out = {k: vals[i] for i, k in enumerate(errs)}
     out["perm_exact"] = vals[-1] == 0.0
+    out["d_lmda_max_abs"] = float(np.abs(dl64).max())        # nonzero: the mixing-weight gradient was really exercised
     out["ok"] = bool(out["y"] <= 1e-5 and out["perm_exact"] and all(out[k] <= 1e-4 for k in ("dx", "d_gamma", "d_beta", "d_lmda"))
                      and out["gamma_std"] <= 1e-5 and out["beta_std"] <= 1e-5)
     out["tolerance"] = {"y": 1e-5, "gradients": 1e-4, "norm": "max|a-b| / max|b| over the tensor, max over ranks"}

@@ -92,6 +92,15 @@ enum {
     MAXSTYLE_SWEEP_FORCE_PAIR = 1 << 26       /* ... take it whenever the shape qualifies                           */
 };
 
+/* activation fused in front of the layer: the kernels take the PRE-activation tensor z and apply the
+ * activation to every value as it is loaded, x = act(z); the backward returns dz */
+enum {
+    MAXSTYLE_PRE_NONE = 0,
+    MAXSTYLE_PRE_LEAKY_RELU = 1,  /* x = z > 0 ? z : slope*z -- the LeakyReLU(0.2) that ends res_up_family
+                                     (src/models/ebm/encoder_decoder.py:337-357) in front of layers 0-4            */
+    MAXSTYLE_PRE_SIGMOID = 2      /* x = 1/(1+exp(-z)) -- the decoder's `last_act` in front of layer 5 (:624-630)   */
+};
+
 /* optimiser step fused into the backward epilogue (north_star item 4) */
 enum {
     MAXSTYLE_STEP_NONE = 0,
@@ -207,6 +216,34 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig,
                  int N, int C, int H, int W, int dtype, int layout, int flags, float eps,
                  int stats_sweep, int apply_sweep,
                  void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
+
+/* maxstyle_fwd with its neighbours fused in (NCHW only):
+ *  - `pre_op` / `pre_param`: `z` is the tensor BEFORE the activation that precedes the layer in the reference's decoders
+ *    (MAXSTYLE_PRE_LEAKY_RELU with its negative slope, or MAXSTYLE_PRE_SIGMOID); the layer sees x = act(z) without x ever
+ *    being written to memory -- one full-tensor pass (read z, write x) less than activation + layer;
+ *  - `y_min` / `y_max` (optional, both or neither; [N*C]): per-plane minimum and maximum of y, collected while y is written,
+ *    as order-preserving unsigned integers reduced with atomicMin / atomicMax -- the caller initialises them to 0xffffffff
+ *    and 0; maxstyle_rescale turns them into the reference's rescale_intensity (src/common_utils/basic_operations.py:257-281,
+ *    applied to the loop's output at advanced_triplet_recon_segmentation_model.py:868-869) in one more pass.
+ * Runs as the paired kernel, else as statistics -> tables -> apply.  maxstyle_bwd_act is the matching backward: it recomputes
+ * x = act(z) on the fly and writes dz = dy * A/sig * act'(z). */
+int maxstyle_fwd_act(const void* z, void* y, float* mu, float* sig,
+                     const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
+                     float* gamma_std, float* beta_std, float* scale, float* shift,
+                     int N, int C, int H, int W, int dtype, int layout, int flags, float eps,
+                     int stats_sweep, int apply_sweep, int pre_op, float pre_param, uint32_t* y_min, uint32_t* y_max,
+                     void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
+int maxstyle_bwd_act(const void* dy, const void* z, void* dz,
+                     const float* mu_all, const float* sig_all, int table_ld, int N_global, int row_offset,
+                     const float* scale, const int64_t* perm, const float* lmda,
+                     const float* gamma_std, const float* beta_std, int flags,
+                     float* d_gamma, float* d_beta, float* d_lmda,
+                     const maxstyle_step_t* step,
+                     int N, int C, int H, int W, int dtype, int layout, int sweep, int pre_op, float pre_param,
+                     void* workspace, size_t workspace_bytes, maxstyle_stream_t stream);
+/* out = (y - min) / (max - min + eps) * (new_max - new_min) + new_min per (n,c) plane, min / max as collected by maxstyle_fwd_act. */
+int maxstyle_rescale(const void* y, const uint32_t* y_min, const uint32_t* y_max, void* out, float new_min, float new_max, float eps,
+                     int N, int C, int H, int W, int dtype, maxstyle_stream_t stream);
 
 /* Number of kernels maxstyle_fwd launches for this shape on the current device: 1 (resident or L2 window), 3 (two-pass:
  * stats, tables, apply), 0 for an unsupported shape.  Assumes 16-byte aligned x and y. */

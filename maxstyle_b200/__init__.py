@@ -8,7 +8,9 @@ from .host_pipeline import HostStepPipeline, HostStepResult
 from .executor import StyleLoopExecutor
 from .graphed import GraphedLayerStep
 from .losses import cross_entropy_2D
+from .fused import apply_max_style_fused, rescale_intensity
 
 __all__ = ["MaxStyle", "MixStyle", "FusedStyleOptimizer", "GlobalBatchMaxStyle", "StyleTableExchange", "PeerTableExchange",
-           "HostStepPipeline", "HostStepResult", "StyleLoopExecutor", "GraphedLayerStep", "cross_entropy_2D"]
+           "HostStepPipeline", "HostStepResult", "StyleLoopExecutor", "GraphedLayerStep", "cross_entropy_2D", "apply_max_style_fused",
+           "rescale_intensity"]
 __version__ = "0.1.0"

@@ -19,6 +19,7 @@ F32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
 FLAG_MIX_STYLE, FLAG_NO_NOISE, FLAG_COMPUTE_BATCH_STD, FLAG_NO_CLAMP = 1, 2, 4, 8
 STEP_NONE, STEP_ADAM, STEP_SIGN = 0, 1, 2
+PRE_NONE, PRE_LEAKY_RELU, PRE_SIGMOID = 0, 1, 2
 SWEEP_REVERSE, SWEEP_X_KEEP, SWEEP_X_STREAM, SWEEP_IO_NORMAL, SWEEP_NO_FUSED = 1, 2, 4, 8, 16
 SWEEP_NO_RESIDENT, SWEEP_FORCE_WINDOW, SWEEP_FORCE_RESIDENT, SWEEP_NO_RING, SWEEP_FORCE_RING = 32, 64, 128, 256, 512
 SWEEP_NO_CLUSTER, SWEEP_FORCE_CLUSTER = 1024, 2048
@@ -63,6 +64,13 @@ SIGNATURES = {
     "maxstyle_fwd": (C.c_int, [_vp, _vp, _f32p, _f32p, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
+    "maxstyle_fwd_act": (C.c_int, [_vp, _vp, _f32p, _f32p, _vp, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                   C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "maxstyle_bwd_act": (C.c_int, [_vp, _vp, _vp, _f32p, _f32p, C.c_int, C.c_int, C.c_int, _f32p, _vp, _f32p, _f32p, _f32p,
+                                   C.c_int, _f32p, _f32p, _f32p, C.POINTER(StepStruct),
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _vp, C.c_size_t, _vp]),
+    "maxstyle_rescale": (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "maxstyle_fwd_kernels": (C.c_int, [C.c_int] * 7),
     "maxstyle_fwd_geometry": (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int)]),
     "maxstyle_workspace_status": (C.c_int, [_vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),

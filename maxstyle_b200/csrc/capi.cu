@@ -63,8 +63,17 @@ Sweep sweep_of(const Plan& p, int64_t M, int sweep) {
     g.reverse = (sweep & MAXSTYLE_SWEEP_REVERSE) ? 1 : 0;
     g.in_policy = (sweep & MAXSTYLE_SWEEP_X_KEEP) ? kPolicyKeep : ((sweep & MAXSTYLE_SWEEP_X_STREAM) ? kPolicyStream : kPolicyNormal);
     g.io_policy = (sweep & MAXSTYLE_SWEEP_IO_NORMAL) ? kPolicyNormal : kPolicyStream;
+    g.pre_op = kPreNone; g.pre_param = 0.f;
     return g;
 }
+
+// The activation fused in front of the layer (include/maxstyle_b200.h: MAXSTYLE_PRE_*) and where min / max of y go.
+struct PreOp {
+    int op = kPreNone;
+    float param = 0.f;
+    unsigned int* ymin = nullptr;
+    unsigned int* ymax = nullptr;
+};
 
 // Vector accesses a thread keeps in flight per tensor: sized so the fp32 copies of the loaded
 // values fit a 32-register budget (the kernels run 4 CTAs x 256 threads per SM, 64 regs/thread).
@@ -76,26 +85,31 @@ template <int VEC, int TENSORS> constexpr int vpt_for() {
 // ---- dispatch on (dtype, vector width, group size) ------------------------------------------
 template <typename T, int VEC, int G>
 void launch_stats(const void* x, float* mu, float* sig, TableRef tr, char* ws, const Workspace& w, const Plan& p, int64_t M,
-                  float eps, int sweep, cudaStream_t s) {
+                  float eps, int sweep, cudaStream_t s, const PreOp& pre) {
+    Sweep g = sweep_of(p, M, sweep);
+    g.pre_op = pre.op; g.pre_param = pre.param;
     stats_nchw_kernel<T, VEC, G, vpt_for<VEC, 1>()><<<p.grid, kThreads, 0, s>>>(
         static_cast<const T*>(x), mu, sig, tr, reinterpret_cast<float4*>(ws + w.partials),
-        reinterpret_cast<unsigned long long*>(ws + w.plane_tickets), sweep_of(p, M, sweep), eps);
+        reinterpret_cast<unsigned long long*>(ws + w.plane_tickets), g, eps);
 }
 
 template <typename T, int VEC, int G>
 void launch_apply(const void* x, void* y, const float* mu, TableRef tr, const float* scale, const float* shift, const Plan& p,
-                  int64_t M, int sweep, cudaStream_t s) {
+                  int64_t M, int sweep, cudaStream_t s, const PreOp& pre) {
+    Sweep g = sweep_of(p, M, sweep);
+    g.pre_op = pre.op; g.pre_param = pre.param;
     apply_nchw_kernel<T, VEC, G, vpt_for<VEC, 1>()><<<p.grid, kThreads, 0, s>>>(static_cast<const T*>(x), static_cast<T*>(y), mu, tr,
-                                                                                scale, shift, sweep_of(p, M, sweep));
+                                                                                scale, shift, g, pre.ymin, pre.ymax);
 }
 
 template <typename T, int VEC, int G>
 void launch_bwd(const void* dy, const void* x, void* dx, char* ws, const Workspace& w, const Plan& p, int64_t M,
-                const BwdTables& tb, const StepArgs& st, int sweep, cudaStream_t s) {
+                const BwdTables& tb, const StepArgs& st, int sweep, cudaStream_t s, const PreOp& pre) {
     float4* partials = reinterpret_cast<float4*>(ws + w.partials);
     unsigned long long* tickets = reinterpret_cast<unsigned long long*>(ws + w.sample_tickets);
     int* done = reinterpret_cast<int*>(ws + w.done_counter);
-    const Sweep g = sweep_of(p, M, sweep);
+    Sweep g = sweep_of(p, M, sweep);
+    g.pre_op = pre.op; g.pre_param = pre.param;
     if (dx)
         bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), true><<<p.grid, kThreads, 0, s>>>(
             static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<T*>(dx), partials, tickets, done, g, tb, st);
@@ -111,6 +125,7 @@ Sweep sweep_of_nhwc(const PlanNhwc& p, int N, int64_t M, int sweep) {
     g.reverse = 0;                                              // the NHWC kernels sweep forward only
     g.in_policy = (sweep & MAXSTYLE_SWEEP_X_KEEP) ? kPolicyKeep : ((sweep & MAXSTYLE_SWEEP_X_STREAM) ? kPolicyStream : kPolicyNormal);
     g.io_policy = (sweep & MAXSTYLE_SWEEP_IO_NORMAL) ? kPolicyNormal : kPolicyStream;
+    g.pre_op = kPreNone; g.pre_param = 0.f;
     return g;
 }
 
@@ -223,6 +238,7 @@ struct FwdCall {
     // statistics tables: [n_global, ld] with this rank's rows at row_offset (single GPU: n_global == N, ld == C, no peers)
     int n_global, row_offset, ld;
     PeerTables pt;
+    PreOp pre;
 };
 
 void fill_tables(FusedArgs& a, const FwdCall& f) {
@@ -591,6 +607,7 @@ int try_pair_fwd(const FwdCall& f, const Workspace& w, int sms, int sweep) {
     a.flags = f.flags; a.eps = f.eps;
     a.pol_first = (sweep & MAXSTYLE_SWEEP_X_STREAM) ? kPolicyNormal : kPolicyKeep;       // the piece is re-read microseconds later
     a.pol_second = kPolicyStream; a.pol_out = kPolicyStream;
+    a.pre_op = f.pre.op; a.pre_param = f.pre.param; a.ymin = f.pre.ymin; a.ymax = f.pre.ymax;
     a.mu = f.mu; a.sig = f.sig; a.scale = f.scale; a.shift = f.shift;
     a.n_global = f.n_global; a.row_offset = f.row_offset; a.ld = f.ld;
     a.perm = f.perm; a.lmda = f.lmda; a.gamma_noise = f.gamma_noise; a.beta_noise = f.beta_noise;
@@ -635,9 +652,12 @@ size_t maxstyle_workspace_bytes(int N, int C, int H, int W, int dtype, int layou
     return workspace_layout(N, C, (int64_t)H * W, dtype, is_nhwc(layout, C)).total;
 }
 
-int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, int row_offset, int N, int C, int H, int W,
-                   int dtype, int layout, float eps, int sweep, void* workspace, size_t workspace_bytes,
-                   maxstyle_stream_t stream) {
+}  // extern "C"
+
+namespace {
+int stats_impl(const void* x, float* mu_all, float* sig_all, int table_ld, int row_offset, int N, int C, int H, int W,
+               int dtype, int layout, float eps, int sweep, void* workspace, size_t workspace_bytes,
+               maxstyle_stream_t stream, const PreOp& pre) {
     int rc = check_shape(N, C, H, W, dtype, layout);
     if (rc) return rc;
     if (!x || !mu_all || !sig_all || row_offset < 0 || table_ld < C) return MAXSTYLE_ERR_BAD_ARG;
@@ -648,6 +668,7 @@ int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, i
     if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
     const TableRef tr{C, table_ld, row_offset};
     if (is_nhwc(layout, C)) {
+        if (pre.op != kPreNone) return MAXSTYLE_ERR_UNSUPPORTED;       // the fused activation is built for NCHW
         const PlanNhwc pn = make_plan_nhwc(N, C, M, dtype, common_align(x), sms);
         if (!pn.ok) return MAXSTYLE_ERR_UNSUPPORTED;
         MS_DISPATCH_NHWC(launch_stats_nhwc, dtype, pn, x, mu_all, sig_all, tr, static_cast<char*>(workspace), w, pn, N, M, eps,
@@ -656,8 +677,18 @@ int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, i
     }
     const Plan p = make_plan(N, C, M, dtype, common_align(x), sms);
     MS_DISPATCH(launch_stats, dtype, p, x, mu_all, sig_all, tr, static_cast<char*>(workspace), w, p, M, eps, sweep,
-                static_cast<cudaStream_t>(stream));
+                static_cast<cudaStream_t>(stream), pre);
     return check_launch();
+}
+}  // namespace
+
+extern "C" {
+
+int maxstyle_stats(const void* x, float* mu_all, float* sig_all, int table_ld, int row_offset, int N, int C, int H, int W,
+                   int dtype, int layout, float eps, int sweep, void* workspace, size_t workspace_bytes,
+                   maxstyle_stream_t stream) {
+    return stats_impl(x, mu_all, sig_all, table_ld, row_offset, N, C, H, W, dtype, layout, eps, sweep, workspace, workspace_bytes, stream,
+                      PreOp{});
 }
 
 int maxstyle_tables(const float* mu_all, const float* sig_all, int table_ld, int N_global, int row_offset, int N, int C,
@@ -709,9 +740,12 @@ int maxstyle_tables_p2p(const uint64_t* peers, int rank, int world, uint32_t* ep
     return check_launch();
 }
 
-int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, int row_offset, const float* scale,
-                   const float* shift, int N, int C, int H, int W, int dtype, int layout, int sweep,
-                   maxstyle_stream_t stream) {
+}  // extern "C"
+
+namespace {
+int apply_impl(const void* x, void* y, const float* mu_all, int table_ld, int row_offset, const float* scale,
+               const float* shift, int N, int C, int H, int W, int dtype, int layout, int sweep,
+               maxstyle_stream_t stream, const PreOp& pre) {
     int rc = check_shape(N, C, H, W, dtype, layout);
     if (rc) return rc;
     if (!x || !y || !mu_all || !scale || !shift || row_offset < 0 || table_ld < C) return MAXSTYLE_ERR_BAD_ARG;
@@ -720,6 +754,7 @@ int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, in
     const int64_t M = (int64_t)H * W;
     const TableRef tr{C, table_ld, row_offset};
     if (is_nhwc(layout, C)) {
+        if (pre.op != kPreNone || pre.ymin != nullptr) return MAXSTYLE_ERR_UNSUPPORTED;
         const PlanNhwc pn = make_plan_nhwc(N, C, M, dtype, common_align(x, y), sms);
         if (!pn.ok) return MAXSTYLE_ERR_UNSUPPORTED;
         MS_DISPATCH_NHWC(launch_apply_nhwc, dtype, pn, x, y, mu_all, tr, scale, shift, pn, N, M, sweep,
@@ -728,14 +763,26 @@ int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, in
     }
     const Plan p = make_plan(N, C, M, dtype, common_align(x, y), sms);
     MS_DISPATCH(launch_apply, dtype, p, x, y, mu_all, tr, scale, shift, p, M, sweep,
-                static_cast<cudaStream_t>(stream));
+                static_cast<cudaStream_t>(stream), pre);
     return check_launch();
 }
+}  // namespace
 
-int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* perm, const float* lmda,
-                 const float* gamma_noise, const float* beta_noise, float* gamma_std, float* beta_std, float* scale,
-                 float* shift, int N, int C, int H, int W, int dtype, int layout, int flags, float eps, int stats_sweep,
-                 int apply_sweep, void* workspace, size_t workspace_bytes, maxstyle_stream_t stream) {
+extern "C" {
+
+int maxstyle_apply(const void* x, void* y, const float* mu_all, int table_ld, int row_offset, const float* scale,
+                   const float* shift, int N, int C, int H, int W, int dtype, int layout, int sweep,
+                   maxstyle_stream_t stream) {
+    return apply_impl(x, y, mu_all, table_ld, row_offset, scale, shift, N, C, H, W, dtype, layout, sweep, stream, PreOp{});
+}
+
+}  // extern "C"
+
+namespace {
+int fwd_impl(const void* x, void* y, float* mu, float* sig, const int64_t* perm, const float* lmda,
+             const float* gamma_noise, const float* beta_noise, float* gamma_std, float* beta_std, float* scale,
+             float* shift, int N, int C, int H, int W, int dtype, int layout, int flags, float eps, int stats_sweep,
+             int apply_sweep, void* workspace, size_t workspace_bytes, maxstyle_stream_t stream, const PreOp& pre) {
     int rc = check_shape(N, C, H, W, dtype, layout);
     if (rc) return rc;
     if (!x || !y || !mu || !sig || !scale || !shift) return MAXSTYLE_ERR_BAD_ARG;
@@ -748,7 +795,7 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
         const int sms = sm_count();
         if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
         FwdCall f{x, y, mu, sig, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, M, dtype, flags, eps,
-                  static_cast<char*>(workspace), static_cast<cudaStream_t>(stream), N, 0, C, PeerTables{}};
+                  static_cast<char*>(workspace), static_cast<cudaStream_t>(stream), N, 0, C, PeerTables{}, pre};
         // Five single-kernel forwards, each the default where it measured fastest (profiles/r02_fwd_paths.txt):
         //   resident  planes of 16-108 KB, tensors >= 64 MB (two CTAs share an SM)               -- x crosses L2 -> SM once
         //   paired    steady state (cached batch std), tensors >= 16 MB, any plane >= 8 KB     -- piece re-read from L2 microseconds later
@@ -758,10 +805,12 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
         const int force_any = force_other | (stats_sweep & (MAXSTYLE_SWEEP_FORCE_CLUSTER | MAXSTYLE_SWEEP_FORCE_PAIR));
         const bool first = (flags & MAXSTYLE_COMPUTE_BATCH_STD) != 0;
         const bool pair_allowed = !(stats_sweep & MAXSTYLE_SWEEP_NO_PAIR) && (!force_any || (stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR));
-        if (stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR) {
+        const bool fused_neighbours = pre.op != kPreNone || pre.ymin != nullptr;       // only the paired and the two-pass kernels take them
+        if ((stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR) || (fused_neighbours && pair_allowed)) {
             rc = try_pair_fwd(f, w, sms, stats_sweep);
             if (rc >= 0) return rc;
         }
+        if (fused_neighbours) goto two_pass;
         if (!(stats_sweep & MAXSTYLE_SWEEP_NO_CLUSTER) && (stats_sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER)) {
             rc = try_cluster_fwd(f, w, sms, stats_sweep);
             if (rc >= 0) return rc;
@@ -785,12 +834,37 @@ int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* p
             if (rc >= 0) return rc;
         }
     }
-    rc = maxstyle_stats(x, mu, sig, C, 0, N, C, H, W, dtype, layout, eps, stats_sweep, workspace, workspace_bytes, stream);
+two_pass:
+    rc = stats_impl(x, mu, sig, C, 0, N, C, H, W, dtype, layout, eps, stats_sweep, workspace, workspace_bytes, stream, pre);
     if (rc) return rc;
     rc = maxstyle_tables(mu, sig, C, N, 0, N, C, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, flags, scale, shift,
                          stream);
     if (rc) return rc;
-    return maxstyle_apply(x, y, mu, C, 0, scale, shift, N, C, H, W, dtype, layout, apply_sweep, stream);
+    return apply_impl(x, y, mu, C, 0, scale, shift, N, C, H, W, dtype, layout, apply_sweep, stream, pre);
+}
+}  // namespace
+
+extern "C" {
+
+int maxstyle_fwd(const void* x, void* y, float* mu, float* sig, const int64_t* perm, const float* lmda,
+                 const float* gamma_noise, const float* beta_noise, float* gamma_std, float* beta_std, float* scale,
+                 float* shift, int N, int C, int H, int W, int dtype, int layout, int flags, float eps, int stats_sweep,
+                 int apply_sweep, void* workspace, size_t workspace_bytes, maxstyle_stream_t stream) {
+    return fwd_impl(x, y, mu, sig, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, H, W, dtype, layout, flags,
+                    eps, stats_sweep, apply_sweep, workspace, workspace_bytes, stream, PreOp{});
+}
+
+int maxstyle_fwd_act(const void* z, void* y, float* mu, float* sig, const int64_t* perm, const float* lmda,
+                     const float* gamma_noise, const float* beta_noise, float* gamma_std, float* beta_std, float* scale,
+                     float* shift, int N, int C, int H, int W, int dtype, int layout, int flags, float eps, int stats_sweep,
+                     int apply_sweep, int pre_op, float pre_param, uint32_t* y_min, uint32_t* y_max,
+                     void* workspace, size_t workspace_bytes, maxstyle_stream_t stream) {
+    if (pre_op != MAXSTYLE_PRE_NONE && pre_op != MAXSTYLE_PRE_LEAKY_RELU && pre_op != MAXSTYLE_PRE_SIGMOID) return MAXSTYLE_ERR_BAD_ARG;
+    if ((y_min == nullptr) != (y_max == nullptr)) return MAXSTYLE_ERR_BAD_ARG;
+    PreOp pre;
+    pre.op = pre_op; pre.param = pre_param; pre.ymin = y_min; pre.ymax = y_max;
+    return fwd_impl(z, y, mu, sig, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, H, W, dtype, layout, flags,
+                    eps, stats_sweep, apply_sweep, workspace, workspace_bytes, stream, pre);
 }
 
 int maxstyle_fwd_p2p(const void* x, void* y, float* mu_all, float* sig_all, int table_ld, int N_global, int row_offset,
@@ -817,7 +891,7 @@ int maxstyle_fwd_p2p(const void* x, void* y, float* mu_all, float* sig_all, int 
     pt.rank = rank; pt.world = world; pt.epoch = epoch; pt.done = nullptr;
     pt.error = reinterpret_cast<int*>(static_cast<char*>(workspace) + w.res_error);
     FwdCall f{x, y, mu_all, sig_all, perm, lmda, gamma_noise, beta_noise, gamma_std, beta_std, scale, shift, N, C, M, dtype, flags, eps,
-              static_cast<char*>(workspace), static_cast<cudaStream_t>(stream), N_global, row_offset, table_ld, pt};
+              static_cast<char*>(workspace), static_cast<cudaStream_t>(stream), N_global, row_offset, table_ld, pt, PreOp{}};
     if (!(stats_sweep & MAXSTYLE_SWEEP_NO_PAIR) && !(stats_sweep & (MAXSTYLE_SWEEP_FORCE_WINDOW | MAXSTYLE_SWEEP_FORCE_CLUSTER))) {
         rc = try_pair_fwd(f, w, sms, stats_sweep);
         if (rc >= 0) return rc;
@@ -1016,11 +1090,14 @@ int maxstyle_workspace_status(const void* workspace, size_t workspace_bytes, int
     return flag ? MAXSTYLE_ERR_TIMEOUT : MAXSTYLE_OK;
 }
 
-int maxstyle_bwd(const void* dy, const void* x, void* dx, const float* mu_all, const float* sig_all, int table_ld, int N_global,
-                 int row_offset, const float* scale, const int64_t* perm, const float* lmda, const float* gamma_std,
-                 const float* beta_std, int flags, float* d_gamma, float* d_beta, float* d_lmda, const maxstyle_step_t* step,
-                 int N, int C, int H, int W, int dtype, int layout, int sweep, void* workspace, size_t workspace_bytes,
-                 maxstyle_stream_t stream) {
+}  // extern "C"
+
+namespace {
+int bwd_impl(const void* dy, const void* x, void* dx, const float* mu_all, const float* sig_all, int table_ld, int N_global,
+             int row_offset, const float* scale, const int64_t* perm, const float* lmda, const float* gamma_std,
+             const float* beta_std, int flags, float* d_gamma, float* d_beta, float* d_lmda, const maxstyle_step_t* step,
+             int N, int C, int H, int W, int dtype, int layout, int sweep, void* workspace, size_t workspace_bytes,
+             maxstyle_stream_t stream, const PreOp& pre) {
     int rc = check_shape(N, C, H, W, dtype, layout);
     if (rc) return rc;
     if (!dy || !x || !mu_all || !sig_all || !scale) return MAXSTYLE_ERR_BAD_ARG;
@@ -1039,6 +1116,7 @@ int maxstyle_bwd(const void* dy, const void* x, void* dx, const float* mu_all, c
     tb.row_offset = row_offset; tb.N = N; tb.C = C; tb.flags = flags; tb.ld = table_ld;
     const StepArgs st = to_step_args(step);
     if (is_nhwc(layout, C)) {
+        if (pre.op != kPreNone) return MAXSTYLE_ERR_UNSUPPORTED;
         const PlanNhwc pn = make_plan_nhwc(N, C, M, dtype, common_align(dy, x, dx), sms);
         if (!pn.ok) return MAXSTYLE_ERR_UNSUPPORTED;
         MS_DISPATCH_NHWC(launch_bwd_nhwc, dtype, pn, dy, x, dx, static_cast<char*>(workspace), w, pn, N, M, tb, st, sweep,
@@ -1047,7 +1125,49 @@ int maxstyle_bwd(const void* dy, const void* x, void* dx, const float* mu_all, c
     }
     const Plan p = make_plan(N, C, M, dtype, common_align(dy, x, dx), sms);
     MS_DISPATCH(launch_bwd, dtype, p, dy, x, dx, static_cast<char*>(workspace), w, p, M, tb, st, sweep,
-                static_cast<cudaStream_t>(stream));
+                static_cast<cudaStream_t>(stream), pre);
+    return check_launch();
+}
+}  // namespace
+
+extern "C" {
+
+int maxstyle_bwd(const void* dy, const void* x, void* dx, const float* mu_all, const float* sig_all, int table_ld, int N_global,
+                 int row_offset, const float* scale, const int64_t* perm, const float* lmda, const float* gamma_std,
+                 const float* beta_std, int flags, float* d_gamma, float* d_beta, float* d_lmda, const maxstyle_step_t* step,
+                 int N, int C, int H, int W, int dtype, int layout, int sweep, void* workspace, size_t workspace_bytes,
+                 maxstyle_stream_t stream) {
+    return bwd_impl(dy, x, dx, mu_all, sig_all, table_ld, N_global, row_offset, scale, perm, lmda, gamma_std, beta_std, flags, d_gamma,
+                    d_beta, d_lmda, step, N, C, H, W, dtype, layout, sweep, workspace, workspace_bytes, stream, PreOp{});
+}
+
+int maxstyle_bwd_act(const void* dy, const void* z, void* dz, const float* mu_all, const float* sig_all, int table_ld, int N_global,
+                     int row_offset, const float* scale, const int64_t* perm, const float* lmda, const float* gamma_std,
+                     const float* beta_std, int flags, float* d_gamma, float* d_beta, float* d_lmda, const maxstyle_step_t* step,
+                     int N, int C, int H, int W, int dtype, int layout, int sweep, int pre_op, float pre_param,
+                     void* workspace, size_t workspace_bytes, maxstyle_stream_t stream) {
+    if (pre_op != MAXSTYLE_PRE_NONE && pre_op != MAXSTYLE_PRE_LEAKY_RELU && pre_op != MAXSTYLE_PRE_SIGMOID) return MAXSTYLE_ERR_BAD_ARG;
+    PreOp pre;
+    pre.op = pre_op; pre.param = pre_param;
+    return bwd_impl(dy, z, dz, mu_all, sig_all, table_ld, N_global, row_offset, scale, perm, lmda, gamma_std, beta_std, flags, d_gamma,
+                    d_beta, d_lmda, step, N, C, H, W, dtype, layout, sweep, workspace, workspace_bytes, stream, pre);
+}
+
+int maxstyle_rescale(const void* y, const uint32_t* y_min, const uint32_t* y_max, void* out, float new_min, float new_max, float eps,
+                     int N, int C, int H, int W, int dtype, maxstyle_stream_t stream) {
+    if (!y || !y_min || !y_max || !out || N <= 0 || C <= 0 || H <= 0 || W <= 0) return MAXSTYLE_ERR_BAD_ARG;
+    if (dtype != MAXSTYLE_F32 && dtype != MAXSTYLE_BF16) return MAXSTYLE_ERR_UNSUPPORTED;
+    const int sms = sm_count();
+    if (sms <= 0) return MAXSTYLE_ERR_NO_DEVICE;
+    const int64_t M = (int64_t)H * W, planes = (int64_t)N * C;
+    const int64_t want = planes * ((M + 1023) / 1024), cap = (int64_t)sms * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == MAXSTYLE_F32)
+        rescale_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(y), y_min, y_max, static_cast<float*>(out), new_min, new_max, eps, planes, M);
+    else
+        rescale_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(y), y_min, y_max, static_cast<__nv_bfloat16*>(out),
+                                                           new_min, new_max, eps, planes, M);
     return check_launch();
 }
 

@@ -252,6 +252,54 @@ __device__ __forceinline__ void wait_timed_out(int* error) {
     __trap();
 }
 
+// ----------------------------------------------------------------------------------------
+// Neighbour fusion.  The layer's input is, in the reference's decoders, the output of an activation that
+// is a kernel of its own there: LeakyReLU(0.2) at the end of res_up_family (encoder_decoder.py:337-357) in front of layers
+// 0-4, the sigmoid `last_act` (encoder_decoder.py:624-627) in front of layer 5.  With a pre-op the kernels take the
+// PRE-activation tensor z and apply the activation to every value as it is loaded (x = act(z)); the backward returns dz.
+// ----------------------------------------------------------------------------------------
+enum : int { kPreNone = 0, kPreLeakyRelu = 1, kPreSigmoid = 2 };
+
+__device__ __forceinline__ float pre_apply(float z, int op, float param) {
+    if (op == kPreLeakyRelu) return z > 0.f ? z : z * param;
+    if (op == kPreSigmoid) return 1.0f / (1.0f + expf(-z));                     // torch.sigmoid's formula
+    return z;
+}
+// d act / d z expressed through x = act(z) (the value the kernels hold anyway): leaky relu keeps the sign, sigmoid' = x(1-x)
+__device__ __forceinline__ float pre_grad(float x, int op, float param) {
+    if (op == kPreLeakyRelu) return x > 0.f ? 1.f : param;
+    if (op == kPreSigmoid) return x * (1.f - x);
+    return 1.f;
+}
+template <int N> __device__ __forceinline__ void pre_apply_vec(float (&v)[N], int op, float param) {
+    if (op != kPreNone) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = pre_apply(v[i], op, param);
+    }
+}
+
+// Per-plane min / max of the output (the reference's rescale_intensity that follows layer 5, basic_operations.py:257-281, needs
+// them): floats mapped to unsigned integers of the same order, so atomicMin / atomicMax do the reduction.  The caller
+// initialises the arrays to 0xffffffff (min) and 0 (max).
+__device__ __forceinline__ unsigned int ordered_bits(float f) {
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_float(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u ^ 0x80000000u) : ~u);
+}
+__device__ __forceinline__ void warp_minmax_publish(float mn, float mx, unsigned int* ymin, unsigned int* ymax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {
+        atomicMin(ymin, ordered_bits(mn));
+        atomicMax(ymax, ordered_bits(mx));
+    }
+}
+
 // Broadcast a flag computed by the group's first thread to the whole group.
 template <int G> __device__ __forceinline__ bool group_bcast(bool flag, Scratch& s) {
     if constexpr (G > 32) {

@@ -58,6 +58,8 @@ struct Sweep {
                       // sweep over the same tensor meets the lines that are still in L2 first)
     int in_policy;    // L2 policy of the loads of the tensor that other kernels of the layer re-read (x)
     int io_policy;    // L2 policy of everything else (dy loads, y / dx stores)
+    int pre_op;       // activation applied to x as it is loaded (kPreNone / kPreLeakyRelu / kPreSigmoid): x = act(z)
+    float pre_param;  // negative slope of the leaky relu
 };
 
 template <int G> struct GroupIdx {
@@ -157,7 +159,7 @@ stats_nchw_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
     Piece pc;
     while (it.next(pc)) {
         const T* base = x + pc.plane * g.M;
-        const float K = to_f32<T>(__ldg(base));
+        const float K = pre_apply(to_f32<T>(__ldg(base)), g.pre_op, g.pre_param);
         Moments acc{0.f, 0.f, 0.f};
         const int len = pc.v1 - pc.v0;
         const Batches<G, VPT> bt(pc, g.reverse != 0);
@@ -165,7 +167,7 @@ stats_nchw_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
             const T* p = base + (int64_t)(bt.begin(i) + t) * VEC;
             float val[VPT][VEC];
 #pragma unroll
-            for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(p + (int64_t)j * G * VEC, val[j], pol);
+            for (int j = 0; j < VPT; ++j) { Vec<T, VEC>::load(p + (int64_t)j * G * VEC, val[j], pol); pre_apply_vec(val[j], g.pre_op, g.pre_param); }
             float s = 0.f;
 #pragma unroll
             for (int j = 0; j < VPT; ++j)
@@ -188,7 +190,7 @@ stats_nchw_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
                 float val[kTail][VEC];
 #pragma unroll
                 for (int j = 0; j < kTail; ++j)
-                    if (lo + j * G < hi) Vec<T, VEC>::load(base + (int64_t)(lo + j * G) * VEC, val[j], pol);
+                    if (lo + j * G < hi) { Vec<T, VEC>::load(base + (int64_t)(lo + j * G) * VEC, val[j], pol); pre_apply_vec(val[j], g.pre_op, g.pre_param); }
 #pragma unroll
                 for (int j = 0; j < kTail; ++j) {
                     if (lo + j * G < hi) {             // each vector is its own mini-batch
@@ -252,7 +254,8 @@ stats_nchw_kernel(const T* __restrict__ x, float* __restrict__ mu, float* __rest
 template <typename T, int VEC, int G, int VPT>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 apply_nchw_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ mu, TableRef tr,
-                  const float* __restrict__ scale, const float* __restrict__ shift, Sweep g) {
+                  const float* __restrict__ scale, const float* __restrict__ shift, Sweep g, unsigned int* __restrict__ ymin,
+                  unsigned int* __restrict__ ymax) {
     const int t = GroupIdx<G>::lane();
     const uint64_t pol_in = make_policy(g.in_policy), pol_out = make_policy(g.io_policy);
     PieceIter<G> it(g, GroupIdx<G>::index());
@@ -261,16 +264,17 @@ apply_nchw_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __res
         const T* src = x + pc.plane * g.M;
         T* dst = y + pc.plane * g.M;
         const float m = __ldg(mu + tr.at(pc.plane)), a = __ldg(scale + pc.plane), b = __ldg(shift + pc.plane);
+        float lo_y = INFINITY, hi_y = -INFINITY;
         const Batches<G, VPT> bt(pc, g.reverse != 0);
         for (int i = 0; i < bt.full; ++i) {
             const int64_t o = (int64_t)(bt.begin(i) + t) * VEC;
             float val[VPT][VEC];
 #pragma unroll
-            for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(src + o + (int64_t)j * G * VEC, val[j], pol_in);
+            for (int j = 0; j < VPT; ++j) { Vec<T, VEC>::load(src + o + (int64_t)j * G * VEC, val[j], pol_in); pre_apply_vec(val[j], g.pre_op, g.pre_param); }
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) val[j][k] = fmaf(val[j][k] - m, a, b);
+                for (int k = 0; k < VEC; ++k) { val[j][k] = fmaf(val[j][k] - m, a, b); lo_y = fminf(lo_y, val[j][k]); hi_y = fmaxf(hi_y, val[j][k]); }
                 Vec<T, VEC>::store(dst + o + (int64_t)j * G * VEC, val[j], pol_out);
             }
         }
@@ -279,16 +283,17 @@ apply_nchw_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __res
             float val[VPT][VEC];
 #pragma unroll
             for (int j = 0; j < VPT; ++j)
-                if (lo + j * G < hi) Vec<T, VEC>::load(src + (int64_t)(lo + j * G) * VEC, val[j], pol_in);
+                if (lo + j * G < hi) { Vec<T, VEC>::load(src + (int64_t)(lo + j * G) * VEC, val[j], pol_in); pre_apply_vec(val[j], g.pre_op, g.pre_param); }
 #pragma unroll
             for (int j = 0; j < VPT; ++j) {
                 if (lo + j * G < hi) {
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) val[j][k] = fmaf(val[j][k] - m, a, b);
+                    for (int k = 0; k < VEC; ++k) { val[j][k] = fmaf(val[j][k] - m, a, b); lo_y = fminf(lo_y, val[j][k]); hi_y = fmaxf(hi_y, val[j][k]); }
                     Vec<T, VEC>::store(dst + (int64_t)(lo + j * G) * VEC, val[j], pol_out);
                 }
             }
         }
+        if (ymin != nullptr) warp_minmax_publish(lo_y, hi_y, ymin + pc.plane, ymax + pc.plane);      // the values are rounded to T on store: exact for fp32
     }
 }
 
@@ -465,6 +470,7 @@ bwd_nchw_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict
             for (int j = 0; j < VPT; ++j) {
                 Vec<T, VEC>::load(gsrc + o + (int64_t)j * G * VEC, gv[j], pol_io);
                 Vec<T, VEC>::load(xsrc + o + (int64_t)j * G * VEC, xv[j], pol_x);
+                pre_apply_vec(xv[j], g.pre_op, g.pre_param);
             }
             float b1 = 0.f, b2 = 0.f;
 #pragma unroll
@@ -477,6 +483,10 @@ bwd_nchw_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict
                 if constexpr (DX) {
 #pragma unroll
                     for (int k = 0; k < VEC; ++k) gv[j][k] *= a;
+                    if (g.pre_op != kPreNone) {                  // dz = dx * act'(z), through x = act(z)
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) gv[j][k] *= pre_grad(xv[j][k], g.pre_op, g.pre_param);
+                    }
                     Vec<T, VEC>::store(dst + o + (int64_t)j * G * VEC, gv[j], pol_io);
                 }
             }
@@ -489,6 +499,7 @@ bwd_nchw_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict
                 float gv[VEC], xv[VEC];
                 Vec<T, VEC>::load(gsrc + (int64_t)lo * VEC, gv, pol_io);
                 Vec<T, VEC>::load(xsrc + (int64_t)lo * VEC, xv, pol_x);
+                pre_apply_vec(xv, g.pre_op, g.pre_param);
                 float b1 = 0.f, b2 = 0.f;
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
@@ -497,7 +508,7 @@ bwd_nchw_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict
                 }
                 if constexpr (DX) {
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) gv[k] *= a;
+                    for (int k = 0; k < VEC; ++k) gv[k] *= a * pre_grad(xv[k], g.pre_op, g.pre_param);
                     Vec<T, VEC>::store(dst + (int64_t)lo * VEC, gv, pol_io);
                 }
                 s1 += b1;

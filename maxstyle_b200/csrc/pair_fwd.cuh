@@ -47,6 +47,9 @@ struct PairArgs {
     int flags;
     float eps;
     int pol_first, pol_second, pol_out;
+    int pre_op;                // activation applied to x as it is loaded (common.cuh: kPre*), x = act(z)
+    float pre_param;
+    unsigned int *ymin, *ymax; // optional [N*C] ordered-integer min / max of y per plane (atomicMin / atomicMax)
     float *mu, *sig;           // [n_global, ld]
     float *scale, *shift;      // [N, C]
     int n_global, row_offset, ld;
@@ -225,18 +228,18 @@ __device__ __noinline__ void pair_resolve(const PairArgs& a, Moments m, float K,
 // ---- the two streaming passes over a piece [v0, v1) of a plane (inlined: ptxas 12.9 crashes on these loops in a
 // non-inlined function); G threads take part ---------------------------------------------------------------------------
 template <typename T, int VEC, int VPT, int G>
-__device__ __forceinline__ Moments pair_pass1(const T* base, int v0, int v1, int pol_kind, int t, float& K_out) {
+__device__ __forceinline__ Moments pair_pass1(const T* base, int v0, int v1, int pol_kind, int t, int pre_op, float pre_param, float& K_out) {
     Piece pc;
     pc.plane = 0; pc.v0 = v0; pc.v1 = v1;
     const Batches<G, VPT> bt(pc, false);
     const uint64_t pol = make_policy(pol_kind);
-    const float K = to_f32<T>(__ldg(base));          // the plane's first element: the same shift in every piece
+    const float K = pre_apply(to_f32<T>(__ldg(base)), pre_op, pre_param);      // the plane's first element: the same shift in every piece
     Moments acc{0.f, 0.f, 0.f};
     for (int b = 0; b < bt.full; ++b) {
         const T* ptr = base + (int64_t)(bt.begin(b) + t) * VEC;
         float val[VPT][VEC];
 #pragma unroll
-        for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(ptr + (int64_t)j * G * VEC, val[j], pol);
+        for (int j = 0; j < VPT; ++j) { Vec<T, VEC>::load(ptr + (int64_t)j * G * VEC, val[j], pol); pre_apply_vec(val[j], pre_op, pre_param); }
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < VPT; ++j)
@@ -258,6 +261,7 @@ __device__ __forceinline__ Moments pair_pass1(const T* base, int v0, int v1, int
         for (int v = bt.ragged_lo() + t; v < rhi; v += G) {      // the ragged end: one vector per thread and trip
             float val[VEC];
             Vec<T, VEC>::load(base + (int64_t)v * VEC, val, pol);
+            pre_apply_vec(val, pre_op, pre_param);
             float s = 0.f;
 #pragma unroll
             for (int e = 0; e < VEC; ++e) { val[e] -= K; s += val[e]; }
@@ -277,7 +281,8 @@ __device__ __forceinline__ Moments pair_pass1(const T* base, int v0, int v1, int
 
 template <typename T, int VEC, int VPT, int G>
 __device__ __forceinline__ void pair_pass2(const T* base, T* dst, int v0, int v1, float mu0, float sc, float shf, int pol_in_kind,
-                                           int pol_out_kind, int t) {
+                                           int pol_out_kind, int t, int pre_op, float pre_param, unsigned int* ymin, unsigned int* ymax) {
+    float lo_y = INFINITY, hi_y = -INFINITY;
     Piece pc;
     pc.plane = 0; pc.v0 = v0; pc.v1 = v1;
     const Batches<G, VPT> bt(pc, false);
@@ -286,11 +291,15 @@ __device__ __forceinline__ void pair_pass2(const T* base, T* dst, int v0, int v1
         const int64_t o = (int64_t)(bt.begin(b) + t) * VEC;
         float val[VPT][VEC];
 #pragma unroll
-        for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(base + o + (int64_t)j * G * VEC, val[j], pol_in);
+        for (int j = 0; j < VPT; ++j) { Vec<T, VEC>::load(base + o + (int64_t)j * G * VEC, val[j], pol_in); pre_apply_vec(val[j], pre_op, pre_param); }
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) val[j][e] = fmaf(val[j][e] - mu0, sc, shf);
+            if (ymin != nullptr) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { lo_y = fminf(lo_y, val[j][e]); hi_y = fmaxf(hi_y, val[j][e]); }
+            }
             Vec<T, VEC>::store(dst + o + (int64_t)j * G * VEC, val[j], pol_out);
         }
     }
@@ -299,11 +308,13 @@ __device__ __forceinline__ void pair_pass2(const T* base, T* dst, int v0, int v1
         for (int v = bt.ragged_lo() + t; v < rhi; v += G) {
             float val[VEC];
             Vec<T, VEC>::load(base + (int64_t)v * VEC, val, pol_in);
+            pre_apply_vec(val, pre_op, pre_param);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) val[e] = fmaf(val[e] - mu0, sc, shf);
+            for (int e = 0; e < VEC; ++e) { val[e] = fmaf(val[e] - mu0, sc, shf); lo_y = fminf(lo_y, val[e]); hi_y = fmaxf(hi_y, val[e]); }
             Vec<T, VEC>::store(dst + (int64_t)v * VEC, val, pol_out);
         }
     }
+    if (ymin != nullptr) warp_minmax_publish(lo_y, hi_y, ymin, ymax);
 }
 
 template <typename T, int VEC, int VPT, int MINB>
@@ -362,7 +373,7 @@ fwd_pair_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_constan
         const int64_t plane = (int64_t)it.n * a.C + it.c;
         const int v0 = it.p * a.piece_vecs, v1 = min(a.nvec, v0 + a.piece_vecs);
         float K;
-        const Moments acc = pair_pass1<T, VEC, VPT, G>(x + plane * a.M, v0, v1, a.pol_first, t, K);
+        const Moments acc = pair_pass1<T, VEC, VPT, G>(x + plane * a.M, v0, v1, a.pol_first, t, a.pre_op, a.pre_param, K);
         const Moments m = group_merge<G>(acc, sh.scratch);             // valid in every thread
         if (t < 32) {
             pair_resolve<VEC>(a, m, K, it.c, it.n, it.p, sh.tag, sh.xtag, &sh.coef);
@@ -372,7 +383,8 @@ fwd_pair_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_constan
         __syncthreads();
         const float4 cf = sh.coef;
         id = sh.next_id;                       // coef / next_id are rewritten only after the next item's block reduction (two barriers)
-        pair_pass2<T, VEC, VPT, G>(x + plane * a.M, y + plane * a.M, v0, v1, cf.x, cf.y, cf.z, a.pol_second, a.pol_out, t);
+        pair_pass2<T, VEC, VPT, G>(x + plane * a.M, y + plane * a.M, v0, v1, cf.x, cf.y, cf.z, a.pol_second, a.pol_out, t, a.pre_op, a.pre_param,
+                                   a.ymin ? a.ymin + plane : nullptr, a.ymax ? a.ymax + plane : nullptr);
     }
     if (t == 0) {
         __threadfence();

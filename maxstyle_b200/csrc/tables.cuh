@@ -203,6 +203,27 @@ step_kernel(const float* __restrict__ d_gamma, const float* __restrict__ d_beta,
         step_update(st.mode, st.maximize, coef, d_lmda[i], st.lmda + i, st.lmda_m + i, st.lmda_v + i);
 }
 
+// rescale_intensity of the reference (src/common_utils/basic_operations.py:257-281) given the per-plane min / max that the forward
+// kernels collected while writing y:  out = (y - min) / (max - min + eps) * (new_max - new_min) + new_min.  One pass (read y,
+// write out) instead of the reference's two reductions + four elementwise kernels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rescale_kernel(const T* __restrict__ y, const unsigned int* __restrict__ ymin, const unsigned int* __restrict__ ymax, T* __restrict__ out,
+               float new_min, float new_max, float eps, int64_t planes, int64_t M) {
+    const int64_t tiles = (M + 1023) / 1024;
+    for (int64_t w = blockIdx.x; w < planes * tiles; w += gridDim.x) {
+        const int64_t plane = w / tiles, tile = w - plane * tiles;
+        const float lo = ordered_float(ymin[plane]), hi = ordered_float(ymax[plane]);
+        const float denom = hi - lo + eps, span = new_max - new_min;
+        const int64_t base = plane * M + tile * 1024;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t e = tile * 1024 + threadIdx.x + 256 * i;
+            if (e < M) out[base + threadIdx.x + 256 * i] = from_f32<T>((to_f32<T>(y[base + threadIdx.x + 256 * i]) - lo) / denom * span + new_min);
+        }
+    }
+}
+
 // Bumps the device-side step counter after step_kernel has finished (same stream).
 __global__ void step_count_kernel(int* step_dev) { *step_dev += 1; }
 

@@ -248,8 +248,11 @@ def style_apply(x, mu_all, row_offset: int, scale, shift, out=None, sweep: Optio
 
 
 def forward_raw(x, perm_dev, lmda, gamma_noise, beta_noise, gamma_std, beta_std, flags: int, eps: float, workspace,
-                out=None, tables=None):
-    """maxstyle_fwd: whole single-GPU forward.  Returns (y, mu, sig, scale, shift)."""
+                out=None, tables=None, pre_op: int = L.PRE_NONE, pre_param: float = 0.0, minmax=None):
+    """maxstyle_fwd: whole single-GPU forward.  Returns (y, mu, sig, scale, shift).
+    `pre_op` != PRE_NONE: x is the PRE-activation tensor and the activation is applied as the kernels load it; `minmax`: a
+    (min, max) pair of int32 [N*C] tensors initialised to -1 (0xffffffff) / 0 that receive the ordered-integer extremes of y
+    (maxstyle_fwd_act)."""
     _require_cuda(x, "x")
     n, c, h, w = x.shape
     if tables is None:
@@ -257,6 +260,16 @@ def forward_raw(x, perm_dev, lmda, gamma_noise, beta_noise, gamma_std, beta_std,
     mu, sig, scale, shift = tables[0], tables[1], tables[2], tables[3]
     y = _like(x) if out is None else out
     layout = layout_of(x)
+    if pre_op != L.PRE_NONE or minmax is not None:
+        rc = L.get_lib().maxstyle_fwd_act(x.data_ptr(), y.data_ptr(), mu.data_ptr(), sig.data_ptr(), _ptr(perm_dev), _ptr(lmda),
+                                          _ptr(gamma_noise), _ptr(beta_noise), _ptr(gamma_std), _ptr(beta_std),
+                                          scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), layout, flags, eps,
+                                          SWEEP_STATS, SWEEP_APPLY, pre_op, pre_param,
+                                          None if minmax is None else minmax[0].data_ptr(), None if minmax is None else minmax[1].data_ptr(),
+                                          workspace.data_ptr(), workspace.numel(), _stream())
+        L.check(rc, "maxstyle_fwd_act")
+        launches.kernels += 1 if (h * w * x.element_size() >= 8192 and (h * w * x.element_size()) % 16 == 0) else 3
+        return y, mu, sig, scale, shift
     rc = L.get_lib().maxstyle_fwd(x.data_ptr(), y.data_ptr(), mu.data_ptr(), sig.data_ptr(), _ptr(perm_dev), _ptr(lmda),
                                   _ptr(gamma_noise), _ptr(beta_noise), _ptr(gamma_std), _ptr(beta_std),
                                   scale.data_ptr(), shift.data_ptr(), n, c, h, w, dtype_code(x), layout, flags, eps,
@@ -268,7 +281,7 @@ def forward_raw(x, perm_dev, lmda, gamma_noise, beta_noise, gamma_std, beta_std,
 
 def backward_raw(dy, x, mu_all, sig_all, row_offset: int, scale, perm_dev, lmda, gamma_std, beta_std, flags: int,
                  workspace, need_dx: bool = True, need_noise_grad: bool = True, need_mix_grad: bool = True,
-                 step: Optional[L.StepStruct] = None, dx_out=None, grads_out=None):
+                 step: Optional[L.StepStruct] = None, dx_out=None, grads_out=None, pre_op: int = L.PRE_NONE, pre_param: float = 0.0):
     """maxstyle_bwd.  Returns (dx | None, d_gamma | None, d_beta | None, d_lmda | None)."""
     _require_cuda(dy, "dy")
     n, c, h, w = x.shape
@@ -284,6 +297,16 @@ def backward_raw(dy, x, mu_all, sig_all, row_offset: int, scale, perm_dev, lmda,
             db = torch.empty(n, c, dtype=torch.float32, device=x.device)
         if need_mix_grad:
             dl = torch.empty(n, dtype=torch.float32, device=x.device)
+    if pre_op != L.PRE_NONE:
+        rc = L.get_lib().maxstyle_bwd_act(dy.data_ptr(), x.data_ptr(), _ptr(dx), mu_all.data_ptr(), sig_all.data_ptr(),
+                                          table_ld(mu_all), mu_all.shape[0], row_offset, scale.data_ptr(), _ptr(perm_dev), _ptr(lmda),
+                                          _ptr(gamma_std), _ptr(beta_std), flags, _ptr(dg), _ptr(db), _ptr(dl),
+                                          C.byref(step) if step is not None else None,
+                                          n, c, h, w, dtype_code(x), layout_of(x), SWEEP_BWD, pre_op, pre_param,
+                                          workspace.data_ptr(), workspace.numel(), _stream())
+        L.check(rc, "maxstyle_bwd_act")
+        launches.kernels += 1
+        return dx, dg, db, dl
     rc = L.get_lib().maxstyle_bwd(dy.data_ptr(), x.data_ptr(), _ptr(dx), mu_all.data_ptr(), sig_all.data_ptr(),
                                   table_ld(mu_all), mu_all.shape[0], row_offset, scale.data_ptr(), _ptr(perm_dev), _ptr(lmda),
                                   _ptr(gamma_std), _ptr(beta_std), flags, _ptr(dg), _ptr(db), _ptr(dl),
@@ -303,7 +326,7 @@ class MaxStyleFunction(torch.autograd.Function):
     state (perm, cached gamma_std/beta_std, flags, workspace, optional fused step)."""
 
     @staticmethod
-    def forward(ctx, x, gamma_noise, beta_noise, lmda, layer):
+    def forward(ctx, x, gamma_noise, beta_noise, lmda, layer, pre_op=L.PRE_NONE, pre_param=0.0, minmax=None):
         x = dense_layout(x)                # NCHW or channels_last, as it came (the output keeps the format)
         flags = layer._flags()
         first = layer.gamma_std is None or layer.beta_std is None
@@ -318,7 +341,9 @@ class MaxStyleFunction(torch.autograd.Function):
             gamma_std, beta_std = layer.gamma_std, layer.beta_std
         ws = layer._workspace_for(x)
         y, mu, sig, scale, shift = forward_raw(x, layer._perm_device(x.device), lmda, gamma_noise, beta_noise,
-                                               gamma_std, beta_std, flags, layer.eps, ws)
+                                               gamma_std, beta_std, flags, layer.eps, ws, pre_op=pre_op, pre_param=pre_param,
+                                               minmax=minmax)
+        ctx.pre = (pre_op, pre_param)
         if first:                      # cached until reset(), like the reference (maxstyle.py:165-168)
             layer.gamma_std, layer.beta_std = gamma_std, beta_std
         layer._redraw_batch_std = False
@@ -333,7 +358,7 @@ class MaxStyleFunction(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         if dy is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None, None, None
         x, lmda = ctx.saved_tensors
         layer = ctx.layer
         mu, sig, scale, gamma_std, beta_std = ctx.tables
@@ -347,12 +372,13 @@ class MaxStyleFunction(torch.autograd.Function):
             dx, dg, db, dl = backward_raw(dy, x, mu, sig, 0, scale, layer._perm_device(x.device), lmda, gamma_std,
                                           beta_std, ctx.flags, layer._workspace_for(x), need_dx=need_dx,
                                           need_noise_grad=(need_g or need_b) and (fused is None or fused.keep_grads),
-                                          need_mix_grad=need_l and (fused is None or fused.keep_grads), step=step)
+                                          need_mix_grad=need_l and (fused is None or fused.keep_grads), step=step,
+                                          pre_op=ctx.pre[0], pre_param=ctx.pre[1])
         n, c = x.shape[0], x.shape[1]
         if fused is not None and not fused.keep_grads:
-            return dx, None, None, None, None
+            return dx, None, None, None, None, None, None, None
         return (dx,
                 dg.view(n, c, 1, 1) if (need_g and dg is not None) else None,
                 db.view(n, c, 1, 1) if (need_b and db is not None) else None,
                 dl.view(n, 1, 1, 1) if (need_l and dl is not None) else None,
-                None)
+                None, None, None, None)

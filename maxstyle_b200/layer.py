@@ -243,4 +243,38 @@ class MaxStyle(nn.Module):
         if self.gamma_noise.device != x.device:
             raise RuntimeError(f"maxstyle_b200: parameters are on {self.gamma_noise.device}, input on {x.device}")
         with torch.cuda.device(x.device):
-            return F.MaxStyleFunction.apply(x, self.gamma_noise, self.beta_noise, self.lmda, self)
+            return F.MaxStyleFunction.apply(x, self.gamma_noise, self.beta_noise, self.lmda, self, L.PRE_NONE, 0.0, None)
+
+    # ------------------------------------------------------------------------------------
+    # neighbour fusion -- an extension, not part of the reference surface
+    # ------------------------------------------------------------------------------------
+    def forward_fused(self, z, pre: str = "leaky_relu", negative_slope: float = 0.2, collect_minmax: bool = False):
+        """`self(act(z))` without materialising act(z): the kernels apply the activation as they load z (and the backward
+        returns dz).  `pre`: "leaky_relu" (the LeakyReLU(0.2) that ends the reference's res_up_family blocks,
+        src/models/ebm/encoder_decoder.py:337-357) or "sigmoid" (the decoder's last_act in front of layer 5, :624-630).
+        `collect_minmax=True` also returns the per-plane (min, max) of y, gathered while y is written, as the int32 tensors
+        `maxstyle_b200.fused.rescale_intensity` takes (the reference rescales the loop's output, model:868-869).
+        Identity cases (inactive draw, batch of 1, ...) return act(z) computed by PyTorch, like `forward` returns x."""
+        if pre not in ("leaky_relu", "sigmoid"):
+            raise ValueError(f"pre must be 'leaky_relu' or 'sigmoid', got {pre!r}")
+        n, c = z.size(0), z.size(1)
+        plane = z.numel() // (n * c) if n * c else 0
+        if (self.rand_p >= self.p) or (not self.mix_style and self.no_noise) or n <= 1 or plane == 1:
+            x = torch.nn.functional.leaky_relu(z, negative_slope) if pre == "leaky_relu" else torch.sigmoid(z)
+            self.data = x
+            return (x, None) if collect_minmax else x
+        assert self.batch_size == n and self.num_feature == c, \
+            f"check input dim, expect ({self.batch_size}, {self.num_feature}, *,*) , got {n}{c}"
+        if not z.is_cuda:
+            raise RuntimeError("maxstyle_b200: MaxStyle.forward_fused got a CPU tensor; the layer runs only as CUDA kernels "
+                               "on a B200 and has no CPU fallback")
+        if not z.is_contiguous():
+            z = z.contiguous()                     # the fused activation is built for NCHW
+        self.data = z
+        minmax = None
+        if collect_minmax:
+            minmax = (torch.full((n * c,), -1, dtype=torch.int32, device=z.device), torch.zeros(n * c, dtype=torch.int32, device=z.device))
+        op = L.PRE_LEAKY_RELU if pre == "leaky_relu" else L.PRE_SIGMOID
+        with torch.cuda.device(z.device):
+            y = F.MaxStyleFunction.apply(z, self.gamma_noise, self.beta_noise, self.lmda, self, op, float(negative_slope), minmax)
+        return (y, minmax) if collect_minmax else y

@@ -129,12 +129,12 @@ class MixStyle(nn.Module):
                                    self._workspace_for(F.dense_layout(x)))
                 state.gamma_std = torch.zeros(1, C, 1, 1, device=x.device)        # unused with NO_NOISE; keeps the one-kernel path
                 state.beta_std = torch.zeros(1, C, 1, 1, device=x.device)
-                return F.MaxStyleFunction.apply(x, None, None, lmda.reshape(B), state)
+                return F.MaxStyleFunction.apply(x, None, None, lmda.reshape(B), state, L.PRE_NONE, 0.0, None)
             elif self.mix == 'gaussian':
                 gaussian_mu = torch.randn(B, C, 1, 1, device=x.device)            # scaled by std_n(mu)  -> beta-like noise
                 gaussian_std = torch.randn(B, C, 1, 1, device=x.device)           # scaled by std_n(sig) -> gamma-like noise
                 state = _CallState(0, self.eps, C, None, self._workspace_for(F.dense_layout(x)))
                 # gamma_std / beta_std stay None: the batch std is taken inside the kernel on every call (:101-102)
-                return F.MaxStyleFunction.apply(x, gaussian_std, gaussian_mu, None, state)
+                return F.MaxStyleFunction.apply(x, gaussian_std, gaussian_mu, None, state, L.PRE_NONE, 0.0, None)
             else:
                 raise NotImplementedError

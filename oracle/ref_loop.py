@@ -60,6 +60,13 @@ def build_solver(ref, network_type="FCN_16_standard_no_STN", use_gpu=True, pretr
     return solver
 
 
+def _widened(cls):
+    """Factory: construct `cls` as usual (float32 draws from the generators), then widen the module to float64."""
+    def make(*a, **k):
+        return cls(*a, **k).double()
+    return make
+
+
 class _CpuLayer:
     """On a CPU box the reference layer must be built with use_gpu=False; the solver does not pass the argument."""
 
@@ -72,9 +79,19 @@ class _CpuLayer:
 
 
 def run_loop(ref, solver, image_v, label_v, layer_cls, *, seed=7, p=1.0, n_iter=5, layers=(3, 4, 5), channel_num=(128, 64, 32, 16, 16, 1),
-             always_use_beta=True, capture=None):
+             always_use_beta=True, capture=None, double=False):
     """solver.generate_max_style_image with `layer_cls` as the MaxStyle class.  `capture`: optional list that receives the
-    layer modules the solver constructed (their parameters / gradients can be inspected afterwards)."""
+    layer modules the solver constructed (their parameters / gradients can be inspected afterwards).  `double=True`: networks,
+    layers (the same float32 draws, widened) and Adam state in float64 -- the yardstick float32 runs are measured against."""
+    if double:
+        for m in solver.model.values():
+            m.double()
+        try:
+            return run_loop(ref, solver, image_v.double(), label_v, _widened(layer_cls), seed=seed, p=p, n_iter=n_iter, layers=layers,
+                            channel_num=channel_num, always_use_beta=always_use_beta, capture=capture)
+        finally:
+            for m in solver.model.values():
+                m.float()
     use_gpu = image_v.is_cuda
     with torch.no_grad():
         (z_i, z_s), _ = solver.fast_predict(image_v)

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""BASELINE config 2 on the REAL reference caller: `AdvancedTripletReconSegmentationModel.generate_max_style_image`
+(src/models/advanced_triplet_recon_segmentation_model.py:458-571) with MaxStyle after the last 3 decoder blocks, the full inner
+style-optimisation loop (n_iter = 5) on one GPU -- once with the reference's own layer, once with maxstyle_b200.MaxStyle swapped
+in by name.  TEST / MEASUREMENT INFRASTRUCTURE (imports oracle/; the unmodified reference comes from oracle/_ref).
+
+  * FCN_16_standard_no_STN with the shipped notebook weights on the notebook's 20 x 192 x 192 batch (the reference's own fixture);
+  * FCN_64_standard_no_STN (kaiming-initialised: no weights ship) on a synthetic 20 x 1 x 224 x 224 batch + random labels --
+    layer 4 then sees BASELINE config 1's 20 x 64 x 224 x 224.
+
+Prints one JSON line per network: loop time with either layer (median of --reps, CUDA-synchronised wall clock), the time
+inside the layers' forward calls (CUDA events in forward hooks), and how far the returned images are apart.
+
+    python tests/loop_config2_ref.py [--reps 5] [--n-iter 5]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+
+def timed_loop(ref, solver, image, label, cls, chans, n_iter, reps, seed=7):
+    from oracle import ref_loop
+    times, fwd_ms, out = [], [], None
+    for r in range(reps + 1):
+        made = []
+        events = []
+
+        def factory(*a, **k):
+            m = cls(*a, **k)
+            m.register_forward_pre_hook(lambda mod, inp: events.append([torch.cuda.Event(enable_timing=True), None]) or events[-1][0].record())
+            m.register_forward_hook(lambda mod, inp, o: (events[-1].__setitem__(1, torch.cuda.Event(enable_timing=True)), events[-1][1].record()) and None)
+            made.append(m)
+            return m
+
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = ref_loop.run_loop(ref, solver, image, label, factory, seed=seed, p=1.0, n_iter=n_iter, channel_num=chans, always_use_beta=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        if r > 0:                                   # first repetition warms cuDNN / allocator up
+            times.append(dt)
+            fwd_ms.append(sum(a.elapsed_time(b) for a, b in events if b is not None))
+    return statistics.median(times), statistics.median(fwd_ms), out, len(events)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--n-iter", type=int, default=5)
+    args = ap.parse_args()
+    from oracle import ref_shims, ref_loop
+    from maxstyle_b200 import MaxStyle
+    ref = ref_shims.load()
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.benchmark = True
+    cases = []
+    solver16 = ref_loop.build_solver(ref, "FCN_16_standard_no_STN", use_gpu=True, pretrained=True)
+    img16, lab16 = ref_loop.load_fixture(ref, dev)
+    cases.append(("FCN_16_standard_no_STN, shipped weights, notebook batch 20x1x192x192", solver16, img16, lab16, (128, 64, 32, 16, 16, 1)))
+    torch.manual_seed(5)
+    solver64 = ref_loop.build_solver(ref, "FCN_64_standard_no_STN", use_gpu=True, pretrained=False, image_size=224)
+    img64 = torch.rand(20, 1, 224, 224, device=dev)
+    lab64 = torch.randint(0, 4, (20, 224, 224), device=dev)
+    cases.append(("FCN_64_standard_no_STN, kaiming init, synthetic batch 20x1x224x224", solver64, img64, lab64, (512, 256, 128, 64, 64, 1)))
+    for name, solver, image, label, chans in cases:
+        t_ref, f_ref, out_ref, calls = timed_loop(ref, solver, image, label, ref.MaxStyle, chans, args.n_iter, args.reps)
+        t_our, f_our, out_our, _ = timed_loop(ref, solver, image, label, MaxStyle, chans, args.n_iter, args.reps)
+        print(json.dumps({
+            "config": "BASELINE config 2 (reference solver, generate_max_style_image, layers [3,4,5], p=1, n_iter=%d): %s" % (args.n_iter, name),
+            "layer_shapes": [[image.shape[0], chans[3], image.shape[2] // 2, image.shape[3] // 2], [image.shape[0], chans[4], image.shape[2], image.shape[3]],
+                             [image.shape[0], 1, image.shape[2], image.shape[3]]],
+            "loop_ms_reference_layer": round(t_ref, 2), "loop_ms_replacement": round(t_our, 2), "loop_speedup": round(t_ref / t_our, 3),
+            "layer_forward_calls": calls, "layer_forward_ms_reference": round(f_ref, 3), "layer_forward_ms_replacement": round(f_our, 3),
+            "layer_forward_speedup": round(f_ref / f_our, 2),
+            "image_max_abs_diff": float((out_ref - out_our).abs().max()), "image_mean_abs_diff": float((out_ref - out_our).abs().mean()),
+            "note": "eager reference loop (torch.optim.Adam, cuDNN convolutions unchanged); the layer's backward runs inside loss.backward() "
+                    "and is not separated out; after 5 Adam steps the float32 trajectories drift (tests/test_gpu_reference_callers.py)"}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

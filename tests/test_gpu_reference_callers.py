@@ -120,11 +120,18 @@ def test_generate_max_style_image_with_replacement(setup, n_iter):
     noise = float((out_r - out_r2).abs().max())
     err = float((out_o - out_r).abs().max())
     mean_err = float((out_o - out_r).abs().mean())
-    print(f"n_iter={n_iter}: |ours - ref| max {err:.3e} mean {mean_err:.3e}; ref run-to-run max {noise:.3e}")
+    # float64 yardstick: the reference loop with everything widened (same draws).  After n_iter Adam(lr=0.1) steps the float32
+    # trajectories of reference AND replacement have drifted from it; the replacement must not drift more than the reference.
+    out_t = ref_loop.run_loop(ref, solver, image, label, ref.MaxStyle, seed=seed, p=1.0, n_iter=n_iter)  if n_iter == 0 else \
+        ref_loop.run_loop(ref, solver, image, label, ref.MaxStyle, seed=seed, p=1.0, n_iter=n_iter, double=True)
+    dr_max, dr_mean = float((out_r.double() - out_t.double()).abs().max()), float((out_r.double() - out_t.double()).abs().mean())
+    do_max, do_mean = float((out_o.double() - out_t.double()).abs().max()), float((out_o.double() - out_t.double()).abs().mean())
+    print(f"n_iter={n_iter}: |ours - ref| max {err:.3e} mean {mean_err:.3e}; ref run-to-run max {noise:.3e}; vs float64 loop: "
+          f"reference max {dr_max:.3e} mean {dr_mean:.3e}, replacement max {do_max:.3e} mean {do_mean:.3e}")
     # images live in [0, 1] (sigmoid output)
     bound = {0: 1e-5, 1: 2e-4, 5: 5e-3}[n_iter]
-    assert err <= max(bound, 10 * noise), f"n_iter={n_iter}: max abs err {err:.3e} (ref run-to-run {noise:.3e})"
-    assert mean_err <= bound / 10 + 10 * noise
+    assert err <= max(bound, 10 * noise, 3 * dr_max), f"n_iter={n_iter}: max abs err {err:.3e} (reference's own float32 drift {dr_max:.3e})"
+    assert do_mean <= max(bound / 10, 3 * dr_mean), f"n_iter={n_iter}: mean drift {do_mean:.3e} vs the reference's {dr_mean:.3e}"
     for m_r, m_o in zip(made_r, made_o):
         for name in ("gamma_noise", "beta_noise", "lmda"):
             a, b = getattr(m_o, name).detach(), getattr(m_r, name).detach()
