@@ -63,7 +63,7 @@ Sweep sweep_of(const Plan& p, int64_t M, int sweep) {
     g.reverse = (sweep & MAXSTYLE_SWEEP_REVERSE) ? 1 : 0;
     g.in_policy = (sweep & MAXSTYLE_SWEEP_X_KEEP) ? kPolicyKeep : ((sweep & MAXSTYLE_SWEEP_X_STREAM) ? kPolicyStream : kPolicyNormal);
     g.io_policy = (sweep & MAXSTYLE_SWEEP_IO_NORMAL) ? kPolicyNormal : kPolicyStream;
-    g.pre_op = kPreNone; g.pre_param = 0.f;
+    g.pre_op = kPreNone; g.pre_param = 0.f; g.vslices = 0;
     return g;
 }
 
@@ -110,11 +110,14 @@ void launch_bwd(const void* dy, const void* x, void* dx, char* ws, const Workspa
     int* done = reinterpret_cast<int*>(ws + w.done_counter);
     Sweep g = sweep_of(p, M, sweep);
     g.pre_op = pre.op; g.pre_param = pre.param;
+    // CTA mode: p.grid may be a multiple of what fits on the device (make_plan's `oversub`); the resident CTAs share the slices
+    int grid = p.grid;
+    if (G > 32 && p.resident > 0 && p.grid > p.resident) { g.vslices = p.grid; grid = p.resident; }
     if (dx)
-        bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), true><<<p.grid, kThreads, 0, s>>>(
+        bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), true><<<grid, kThreads, 0, s>>>(
             static_cast<const T*>(dy), static_cast<const T*>(x), static_cast<T*>(dx), partials, tickets, done, g, tb, st);
     else
-        bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), false><<<p.grid, kThreads, 0, s>>>(
+        bwd_nchw_kernel<T, VEC, G, vpt_for<VEC, 2>(), false><<<grid, kThreads, 0, s>>>(
             static_cast<const T*>(dy), static_cast<const T*>(x), nullptr, partials, tickets, done, g, tb, st);
 }
 
@@ -125,7 +128,7 @@ Sweep sweep_of_nhwc(const PlanNhwc& p, int N, int64_t M, int sweep) {
     g.reverse = 0;                                              // the NHWC kernels sweep forward only
     g.in_policy = (sweep & MAXSTYLE_SWEEP_X_KEEP) ? kPolicyKeep : ((sweep & MAXSTYLE_SWEEP_X_STREAM) ? kPolicyStream : kPolicyNormal);
     g.io_policy = (sweep & MAXSTYLE_SWEEP_IO_NORMAL) ? kPolicyNormal : kPolicyStream;
-    g.pre_op = kPreNone; g.pre_param = 0.f;
+    g.pre_op = kPreNone; g.pre_param = 0.f; g.vslices = 0;
     return g;
 }
 
@@ -258,7 +261,7 @@ void launch_fused(const FwdCall& f, const FusedArgs& a, int grid) {
 // 133.6 to 132.4 us at 64 MB and costs the forward as much (profiles/r01_keep.txt) -- the backward is not limited by its
 // DRAM reads of x.
 int keep_from_channel(int N, int C, int64_t M, int dtype, bool keep_x) {
-    static const int64_t keep_bytes = env_or("MAXSTYLE_FUSED_KEEP_MB", 0, 1 << 20);
+    const int64_t keep_bytes = tunables().fused_keep_bytes;
     if (!keep_x || keep_bytes <= 0) return C;
     const int64_t channel_bytes = (int64_t)N * M * elem_size(dtype);
     const int64_t k = keep_bytes / channel_bytes;
@@ -379,6 +382,12 @@ int launch_resident(const FwdCall& f, ResidentArgs& a, const ResidentPlan& rp, i
     const int64_t cap = (int64_t)sms * k;
     const int grid = (int)(a.total_items < cap ? a.total_items : cap);
     if (f.N > grid) return -1;                                 // the co-residency argument needs N <= grid
+    {   // same start-up stagger as the paired forward (try_pair_fwd): the CTAs of an SM load and store out of phase
+        const int64_t env_ns = tunables().pair_stagger_ns;
+        const int64_t ns = env_ns > 0 ? env_ns : (env_ns < 0 || k < 2 || a.total_items < 3ll * grid ? 0 : 3000);
+        a.stagger_cycles = (int)(ns * 19 / 10);
+        a.slot_div = sms;
+    }
     kern<<<grid, THREADS, rp.smem, f.stream>>>(static_cast<const T*>(f.x), static_cast<T*>(f.y), a);
     return check_launch();
 }
@@ -466,9 +475,9 @@ struct ClusterNeeds { int N; bool whole_channel; bool has_partner; };
 // Pick cluster size and pieces: every SM busy, >= 3-4 stages per CTA, few idle slots in the last round, few pieces.
 template <typename T>
 ClusterChoice choose_cluster(int64_t planes, int64_t M, int dtype, int align, int sms, int sweep, ClusterNeeds need) {
-    static const int64_t env_cs = env_or("MAXSTYLE_CLUSTER_CS", 0, 1);
-    static const int64_t env_stages = env_or("MAXSTYLE_CLUSTER_STAGES", kClusterMaxStages, 1);
-    static const int64_t env_pieces = env_or("MAXSTYLE_CLUSTER_PIECES", 0, 1);
+    const int64_t env_cs = tunables().cluster_cs;
+    const int64_t env_stages = tunables().cluster_stages;
+    const int64_t env_pieces = tunables().cluster_pieces;
     const int sweep_cs = (sweep >> MAXSTYLE_SWEEP_CLUSTER_SIZE_SHIFT) & 15, sweep_stages = (sweep >> MAXSTYLE_SWEEP_CLUSTER_STAGES_SHIFT) & 7;
     const int sweep_pieces = (sweep >> MAXSTYLE_SWEEP_CLUSTER_PIECES_SHIFT) & 63;
     const int64_t force_cs = sweep_cs ? sweep_cs : env_cs;
@@ -513,7 +522,7 @@ int launch_cluster(const FwdCall& f, const Workspace& w, int sms, bool force, in
     if (!ch.plan.ok || ch.clusters <= 0) return -1;
     const ClusterPlan& cp = ch.plan;
     if (cp.pieces > cluster_max_pieces(f.M, f.dtype)) return -1;
-    static const int64_t enabled = env_or("MAXSTYLE_CLUSTER", 1, 1);
+    const int64_t enabled = tunables().cluster_enabled;
     if (!force && enabled == 2) return -1;                    // MAXSTYLE_CLUSTER=2: only when forced
     ClusterArgs a{};
     a.N = f.N; a.C = f.C; a.M = f.M;
@@ -547,7 +556,7 @@ int try_cluster_fwd(const FwdCall& f, const Workspace& w, int sms, int sweep) {
     const bool force = (sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER) != 0;
     const int64_t pb = f.M * elem_size(f.dtype);
     if (f.N < 2 || pb < kClusterMinPlaneBytes) return -1;
-    static const int64_t enabled = env_or("MAXSTYLE_CLUSTER", 1, 1);
+    const int64_t enabled = tunables().cluster_enabled;
     if (!force && enabled == 0) return -1;
     return f.dtype == MAXSTYLE_F32 ? launch_cluster<float>(f, w, sms, force, sweep) : launch_cluster<__nv_bfloat16>(f, w, sms, force, sweep);
 }
@@ -555,7 +564,7 @@ int try_cluster_fwd(const FwdCall& f, const Workspace& w, int sms, int sweep) {
 // ---- paired forward -----------------------------------------------------------------------------------
 template <typename T, int VEC>
 void launch_pair(const FwdCall& f, const PairArgs& a, int grid) {
-    static const int64_t minb = env_or("MAXSTYLE_PAIR_MINB", 4, 1);      // CTAs per SM the register budget is set for (3: 85 registers, 4: 64)
+    const int64_t minb = tunables().pair_minb;
     const T* xs = static_cast<const T*>(f.x);
     T* ys = static_cast<T*>(f.y);
     constexpr int VPT = vpt_for<VEC, 1>();
@@ -568,9 +577,9 @@ struct PairChoice { PairPlan plan; int grid; int use_order; };
 PairChoice choose_pair(int N, int C, int64_t M, int dtype, int align, int sms, int sweep, bool whole_channel, bool has_partner) {
     PairChoice ch{};
     const int force_pieces = (sweep >> MAXSTYLE_SWEEP_CLUSTER_PIECES_SHIFT) & 63;
-    ch.plan = make_pair_plan(M, dtype, align, force_pieces);
+    ch.plan = make_pair_plan(M, dtype, align, force_pieces, (int64_t)N * C);
     if (!ch.plan.ok) return ch;
-    static const int64_t minb = env_or("MAXSTYLE_PAIR_MINB", 4, 1);
+    const int64_t minb = tunables().pair_minb;
     const int64_t items = (int64_t)N * C * ch.plan.pieces, cap = (int64_t)sms * (minb == 3 ? 3 : 4);
     ch.grid = (int)(items < cap ? items : cap);
     // an item waits for items within W positions: grid > W keeps a CTA free for the lowest missing one
@@ -579,7 +588,7 @@ PairChoice choose_pair(int N, int C, int64_t M, int dtype, int align, int sms, i
         ch.use_order = 1;
     }
     // experiment: walk the samples in cycle order whenever it is allowed (partner planes are then taken back to back)
-    static const int64_t force_order = env_or("MAXSTYLE_PAIR_ORDER", 0, 1);
+    const int64_t force_order = tunables().pair_order;
     if (force_order == 1 && !whole_channel && has_partner && N <= kPairMaxN && 2 * ch.plan.pieces < ch.grid) ch.use_order = 1;
     return ch;
 }
@@ -593,7 +602,7 @@ bool pair_preferred(int N, int C, int64_t M, int dtype) {
 // Same contract as try_fused_fwd.
 int try_pair_fwd(const FwdCall& f, const Workspace& w, int sms, int sweep) {
     const bool force = (sweep & MAXSTYLE_SWEEP_FORCE_PAIR) != 0;
-    static const int64_t enabled = env_or("MAXSTYLE_PAIR", 1, 1);
+    const int64_t enabled = tunables().pair_enabled;
     if (!force && enabled != 1) return -1;
     if (f.N < 2) return -1;
     const bool multi = f.pt.world > 1, first = (f.flags & MAXSTYLE_COMPUTE_BATCH_STD) != 0;
@@ -604,6 +613,16 @@ int try_pair_fwd(const FwdCall& f, const Workspace& w, int sms, int sweep) {
     a.N = f.N; a.C = f.C; a.M = f.M;
     a.nvec = ch.plan.nvec; a.pieces = ch.plan.pieces; a.piece_vecs = ch.plan.piece_vecs; a.use_order = ch.use_order;
     a.total_items = (int64_t)f.N * f.C * ch.plan.pieces;
+    // The k-th CTA of an SM starts k * 3 us late when every CTA has >= 3 items to go through: started together, the CTAs read
+    // (pass 1) and write (pass 2) in a common rhythm, and HBM moves pure reads or pure writes ~20 % slower than a mix
+    // (config 1: 110.1 -> 102.7 us, 64x32x512x512: 923 -> 868 us; profiles/r02_fwd_experiments.txt).  MAXSTYLE_PAIR_STAGGER_NS
+    // overrides the delay (-1: none).
+    {
+        const int64_t env_ns = tunables().pair_stagger_ns;
+        const int64_t ns = env_ns > 0 ? env_ns : (env_ns < 0 || a.total_items < 3ll * ch.grid ? 0 : 3000);
+        a.stagger_cycles = (int)(ns * 19 / 10);
+        a.slot_div = sms;
+    }
     a.flags = f.flags; a.eps = f.eps;
     a.pol_first = (sweep & MAXSTYLE_SWEEP_X_STREAM) ? kPolicyNormal : kPolicyKeep;       // the piece is re-read microseconds later
     a.pol_second = kPolicyStream; a.pol_out = kPolicyStream;
@@ -1016,7 +1035,7 @@ int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int 
     const int force_other = stats_sweep & (MAXSTYLE_SWEEP_FORCE_RESIDENT | MAXSTYLE_SWEEP_FORCE_RING | MAXSTYLE_SWEEP_FORCE_WINDOW);
     const int force_any = force_other | (stats_sweep & (MAXSTYLE_SWEEP_FORCE_CLUSTER | MAXSTYLE_SWEEP_FORCE_PAIR));
     auto pair_ok = [&]() {
-        static const int64_t pair_enabled = env_or("MAXSTYLE_PAIR", 1, 1);
+        const int64_t pair_enabled = tunables().pair_enabled;
         if (N < 2 || (!(stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR) && pair_enabled != 1)) return false;
         const PairChoice ch = choose_pair(N, C, M, dtype, 32, sm_count(), stats_sweep, false, true);
         return ch.plan.ok && ch.plan.pieces <= workspace_layout(N, C, M, dtype).max_pieces;
@@ -1123,7 +1142,7 @@ int bwd_impl(const void* dy, const void* x, void* dx, const float* mu_all, const
                          static_cast<cudaStream_t>(stream));
         return check_launch();
     }
-    const Plan p = make_plan(N, C, M, dtype, common_align(dy, x, dx), sms);
+    const Plan p = make_plan(N, C, M, dtype, common_align(dy, x, dx), sms, (int)tunables().bwd_oversub);
     MS_DISPATCH(launch_bwd, dtype, p, dy, x, dx, static_cast<char*>(workspace), w, p, M, tb, st, sweep,
                 static_cast<cudaStream_t>(stream), pre);
     return check_launch();

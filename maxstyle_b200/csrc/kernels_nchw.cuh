@@ -60,6 +60,7 @@ struct Sweep {
     int io_policy;    // L2 policy of everything else (dy loads, y / dx stores)
     int pre_op;       // activation applied to x as it is loaded (kPreNone / kPreLeakyRelu / kPreSigmoid): x = act(z)
     float pre_param;  // negative slope of the leaky relu
+    int vslices;      // backward, CTA mode: number of slices of `per` vectors; the CTAs take them from a ticket counter (0: one per CTA)
 };
 
 template <int G> struct GroupIdx {
@@ -448,7 +449,20 @@ bwd_nchw_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict
     const int t = GroupIdx<G>::lane();
     const uint64_t pol_x = make_policy(g.in_policy), pol_io = make_policy(g.io_policy);
     const unsigned long long sample_total = (unsigned long long)tb.C * (unsigned long long)g.nvec;
-    PieceIter<G> it(g, GroupIdx<G>::index());
+    // CTA mode with g.vslices > gridDim.x: the tensor is cut into more slices than there are CTAs; a CTA starts on slice
+    // blockIdx.x and takes further ones from a ticket counter (fetched a slice ahead), so the CTAs that the memory system
+    // serves faster do more of them and all finish together -- with one static slice per CTA the last 15 % of the kernel ran at
+    // half the DRAM throughput (profiles/r02_pm_series.txt).  Partial slots are indexed by slice, not by CTA: results do not
+    // depend on who computed what.
+    __shared__ int next_slice[2];
+    int par = 0;
+    unsigned int* slice_ticket = reinterpret_cast<unsigned int*>(done_counter) + 16;      // bytes 64 / 128 of the counter block
+    unsigned int* slice_exits = reinterpret_cast<unsigned int*>(done_counter) + 32;
+    const bool dynamic = G > 32 && g.vslices > (int)gridDim.x;
+    int64_t gi = GroupIdx<G>::index();
+  for (;;) {
+    if (dynamic && t == 0) next_slice[par] = (int)(gridDim.x + atomicAdd(slice_ticket, 1u));
+    PieceIter<G> it(g, gi);
     Piece pc;
     int pending_n = -1;                    // sample whose finished vectors have not been ticketed yet
     unsigned long long pending = 0;
@@ -518,7 +532,7 @@ bwd_nchw_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict
         group_sum2<G>(s1, s2, scratch);
         if (t == 0) {
             int k = 0;
-            if constexpr (G > 32) k = (int)(blockIdx.x - plane_share(g, pc.plane).first);
+            if constexpr (G > 32) k = (int)(gi - plane_share(g, pc.plane).first);
             partials[pc.plane * g.slots + k] = make_float4(s1, s2, 0.f, 0.f);
         }
         pending_n = n;
@@ -532,6 +546,15 @@ bwd_nchw_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict
             pending = 0;
         }
     }
+    if (!dynamic) break;
+    __syncthreads();
+    gi = next_slice[par];                  // rewritten two slices later, behind this barrier
+    par ^= 1;
+    if (gi >= g.vslices) {
+        if (t == 0 && atomicAdd(slice_exits, 1u) == gridDim.x - 1u) { *slice_ticket = 0u; *slice_exits = 0u; }      // last CTA out
+        break;
+    }
+  }
 }
 
 }  // namespace ms

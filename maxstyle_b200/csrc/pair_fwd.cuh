@@ -43,6 +43,7 @@ struct PairArgs {
     int pieces;                // P
     int piece_vecs;            // vectors per piece (the last piece of a plane may be shorter)
     int use_order;             // samples visited in cycle order of perm
+    int stagger_cycles, slot_div;   // CTA b starts (b / slot_div) * stagger_cycles late, so the CTAs of an SM run out of phase
     int64_t total_items;       // N * C * P
     int flags;
     float eps;
@@ -226,25 +227,51 @@ __device__ __noinline__ void pair_resolve(const PairArgs& a, Moments m, float K,
 }
 
 // ---- the two streaming passes over a piece [v0, v1) of a plane (inlined: ptxas 12.9 crashes on these loops in a
-// non-inlined function); G threads take part ---------------------------------------------------------------------------
+// non-inlined function); G threads take part.  A pass is a chain of round trips (issue VPT loads per thread, wait, compute), and
+// with pieces of ~3 batches every round trip saved is ~8 % of the item, so:
+//   * the ragged end of the piece (fewer than G*VPT vectors) is loaded in the shadow of the first batch's loads, not after them;
+//   * the LAST batch of pass 1 stays in registers (`held`) across the publish / partner gap and is the FIRST batch pass 2
+//     writes -- pass 2 walks the piece backwards, so it re-reads one batch less from L2 and starts storing without a load.
 template <typename T, int VEC, int VPT, int G>
-__device__ __forceinline__ Moments pair_pass1(const T* base, int v0, int v1, int pol_kind, int t, int pre_op, float pre_param, float& K_out) {
-    Piece pc;
-    pc.plane = 0; pc.v0 = v0; pc.v1 = v1;
-    const Batches<G, VPT> bt(pc, false);
+__device__ __forceinline__ void pair_load_batch(const T* base, int first_vec, int t, uint64_t pol, float (&val)[VPT][VEC]) {
+    const T* ptr = base + (int64_t)(first_vec + t) * VEC;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) Vec<T, VEC>::load(ptr + (int64_t)j * G * VEC, val[j], pol);
+}
+
+template <typename T, int VEC, int VPT, int G>
+__device__ __forceinline__ Moments pair_pass1(const T* base, int v0, int v1, int pol_kind, int t, int pre_op, float pre_param, float& K_out,
+                                              float (&held)[VPT][VEC]) {
+    constexpr int kStep = G * VPT;
+    const int full = (v1 - v0) / kStep, tail_lo = v0 + full * kStep;
     const uint64_t pol = make_policy(pol_kind);
     const float K = pre_apply(to_f32<T>(__ldg(base)), pre_op, pre_param);      // the plane's first element: the same shift in every piece
     Moments acc{0.f, 0.f, 0.f};
-    for (int b = 0; b < bt.full; ++b) {
-        const T* ptr = base + (int64_t)(bt.begin(b) + t) * VEC;
-        float val[VPT][VEC];
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) { Vec<T, VEC>::load(ptr + (int64_t)j * G * VEC, val[j], pol); pre_apply_vec(val[j], pre_op, pre_param); }
+    if (full > 0) pair_load_batch<T, VEC, VPT, G>(base, v0, t, pol, held);
+    for (int v = tail_lo + t; v < v1; v += G) {                  // the ragged end: one vector per thread and trip
+        float val[VEC];
+        Vec<T, VEC>::load(base + (int64_t)v * VEC, val, pol);
+        pre_apply_vec(val, pre_op, pre_param);
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < VPT; ++j)
+        for (int e = 0; e < VEC; ++e) { val[e] -= K; s += val[e]; }
+        Moments bm;
+        bm.n = (float)VEC;
+        bm.mean = s * (1.0f / (float)VEC);
+        float qq = 0.f;
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) { val[j][e] -= K; s += val[j][e]; }
+        for (int e = 0; e < VEC; ++e) { const float d = val[e] - bm.mean; qq = fmaf(d, d, qq); }
+        bm.m2 = qq;
+        acc = merge_fast(acc, bm);
+    }
+    for (int b = 0; b < full; ++b) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+            pre_apply_vec(held[j], pre_op, pre_param);           // held keeps act(z): pass 2 writes from it
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) s += held[j][e] - K;
+        }
         Moments bm;
         bm.n = (float)(VPT * VEC);
         bm.mean = s * (1.0f / (float)(VPT * VEC));
@@ -252,28 +279,10 @@ __device__ __forceinline__ Moments pair_pass1(const T* base, int v0, int v1, int
 #pragma unroll
         for (int j = 0; j < VPT; ++j)
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) { const float d = val[j][e] - bm.mean; qq = fmaf(d, d, qq); }
+            for (int e = 0; e < VEC; ++e) { const float d = (held[j][e] - K) - bm.mean; qq = fmaf(d, d, qq); }
         bm.m2 = qq;
         acc = merge_fast(acc, bm);
-    }
-    if (bt.rem) {
-        const int rhi = bt.ragged_hi();
-        for (int v = bt.ragged_lo() + t; v < rhi; v += G) {      // the ragged end: one vector per thread and trip
-            float val[VEC];
-            Vec<T, VEC>::load(base + (int64_t)v * VEC, val, pol);
-            pre_apply_vec(val, pre_op, pre_param);
-            float s = 0.f;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) { val[e] -= K; s += val[e]; }
-            Moments bm;
-            bm.n = (float)VEC;
-            bm.mean = s * (1.0f / (float)VEC);
-            float qq = 0.f;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) { const float d = val[e] - bm.mean; qq = fmaf(d, d, qq); }
-            bm.m2 = qq;
-            acc = merge_fast(acc, bm);
-        }
+        if (b + 1 < full) pair_load_batch<T, VEC, VPT, G>(base, v0 + (b + 1) * kStep, t, pol, held);
     }
     K_out = K;
     return acc;
@@ -281,31 +290,40 @@ __device__ __forceinline__ Moments pair_pass1(const T* base, int v0, int v1, int
 
 template <typename T, int VEC, int VPT, int G>
 __device__ __forceinline__ void pair_pass2(const T* base, T* dst, int v0, int v1, float mu0, float sc, float shf, int pol_in_kind,
-                                           int pol_out_kind, int t, int pre_op, float pre_param, unsigned int* ymin, unsigned int* ymax) {
+                                           int pol_out_kind, int t, int pre_op, float pre_param, unsigned int* ymin, unsigned int* ymax,
+                                           float (&held)[VPT][VEC]) {
+    constexpr int kStep = G * VPT;
     float lo_y = INFINITY, hi_y = -INFINITY;
-    Piece pc;
-    pc.plane = 0; pc.v0 = v0; pc.v1 = v1;
-    const Batches<G, VPT> bt(pc, false);
+    const int full = (v1 - v0) / kStep, tail_lo = v0 + full * kStep;
     const uint64_t pol_in = make_policy(pol_in_kind), pol_out = make_policy(pol_out_kind);
-    for (int b = 0; b < bt.full; ++b) {
-        const int64_t o = (int64_t)(bt.begin(b) + t) * VEC;
-        float val[VPT][VEC];
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) { Vec<T, VEC>::load(base + o + (int64_t)j * G * VEC, val[j], pol_in); pre_apply_vec(val[j], pre_op, pre_param); }
+    for (int b = full - 1; b >= 0; --b) {                        // batch full-1 is still in registers from pass 1
+        const int64_t o = (int64_t)(v0 + b * kStep + t) * VEC;
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
+            if (b != full - 1) pre_apply_vec(held[j], pre_op, pre_param);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) val[j][e] = fmaf(val[j][e] - mu0, sc, shf);
+            for (int e = 0; e < VEC; ++e) held[j][e] = fmaf(held[j][e] - mu0, sc, shf);
             if (ymin != nullptr) {
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) { lo_y = fminf(lo_y, val[j][e]); hi_y = fmaxf(hi_y, val[j][e]); }
+                for (int e = 0; e < VEC; ++e) { lo_y = fminf(lo_y, held[j][e]); hi_y = fmaxf(hi_y, held[j][e]); }
             }
-            Vec<T, VEC>::store(dst + o + (int64_t)j * G * VEC, val[j], pol_out);
+            Vec<T, VEC>::store(dst + o + (int64_t)j * G * VEC, held[j], pol_out);
+        }
+        if (b > 0) pair_load_batch<T, VEC, VPT, G>(base, v0 + (b - 1) * kStep, t, pol_in, held);
+        if (b == full - 1) {
+            // the ragged end, in the shadow of the loads just issued
+            for (int v = tail_lo + t; v < v1; v += G) {
+                float val[VEC];
+                Vec<T, VEC>::load(base + (int64_t)v * VEC, val, pol_in);
+                pre_apply_vec(val, pre_op, pre_param);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { val[e] = fmaf(val[e] - mu0, sc, shf); lo_y = fminf(lo_y, val[e]); hi_y = fmaxf(hi_y, val[e]); }
+                Vec<T, VEC>::store(dst + (int64_t)v * VEC, val, pol_out);
+            }
         }
     }
-    if (bt.rem) {
-        const int rhi = bt.ragged_hi();
-        for (int v = bt.ragged_lo() + t; v < rhi; v += G) {
+    if (full == 0) {
+        for (int v = tail_lo + t; v < v1; v += G) {
             float val[VEC];
             Vec<T, VEC>::load(base + (int64_t)v * VEC, val, pol_in);
             pre_apply_vec(val, pre_op, pre_param);
@@ -345,7 +363,13 @@ fwd_pair_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_constan
                 }
             }
         }
-        if (t == 0) { sh.next_id = (long long)atomicAdd(a.queue, 1ull); sh.tag = wtag; sh.xtag = xtag; }
+        if (t == 0) {
+            if (a.stagger_cycles > 0) {                     // the ticket is taken after the delay: nothing waits on a sleeping CTA
+                const long long wait = (long long)(blockIdx.x / a.slot_div) * a.stagger_cycles, t0 = clock64();
+                while (clock64() - t0 < wait) __nanosleep(200);
+            }
+            sh.next_id = (long long)atomicAdd(a.queue, 1ull); sh.tag = wtag; sh.xtag = xtag;
+        }
         if (a.pt.world > 1 && xtag > 1u && t < 32) {
             // Flow control for the two-parity inboxes: this launch overwrites the words of launch xtag-2.  A peer that has published
             // anything in launch xtag-1 has finished launch xtag-2: wait for one word of launch xtag-1 from each peer (its first row,
@@ -373,7 +397,8 @@ fwd_pair_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_constan
         const int64_t plane = (int64_t)it.n * a.C + it.c;
         const int v0 = it.p * a.piece_vecs, v1 = min(a.nvec, v0 + a.piece_vecs);
         float K;
-        const Moments acc = pair_pass1<T, VEC, VPT, G>(x + plane * a.M, v0, v1, a.pol_first, t, a.pre_op, a.pre_param, K);
+        float held[VPT][VEC];                                          // the piece's last batch: loaded in pass 1, written in pass 2
+        const Moments acc = pair_pass1<T, VEC, VPT, G>(x + plane * a.M, v0, v1, a.pol_first, t, a.pre_op, a.pre_param, K, held);
         const Moments m = group_merge<G>(acc, sh.scratch);             // valid in every thread
         if (t < 32) {
             pair_resolve<VEC>(a, m, K, it.c, it.n, it.p, sh.tag, sh.xtag, &sh.coef);
@@ -384,7 +409,7 @@ fwd_pair_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_constan
         const float4 cf = sh.coef;
         id = sh.next_id;                       // coef / next_id are rewritten only after the next item's block reduction (two barriers)
         pair_pass2<T, VEC, VPT, G>(x + plane * a.M, y + plane * a.M, v0, v1, cf.x, cf.y, cf.z, a.pol_second, a.pol_out, t, a.pre_op, a.pre_param,
-                                   a.ymin ? a.ymin + plane : nullptr, a.ymax ? a.ymax + plane : nullptr);
+                                   a.ymin ? a.ymin + plane : nullptr, a.ymax ? a.ymax + plane : nullptr, held);
     }
     if (t == 0) {
         __threadfence();

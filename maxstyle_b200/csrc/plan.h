@@ -30,6 +30,7 @@ struct Plan {
     int64_t planes;   // N*C
     int64_t total;    // planes*nvec
     int64_t per;      // CTA mode: vectors per CTA;  warp mode: planes per warp
+    int resident;     // CTA mode with oversub > 1: CTAs that fit on the device at once (grid slices are shared among them); else 0
 };
 
 inline int elem_size(int dtype) { return dtype == 0 ? 4 : 2; }
@@ -39,8 +40,9 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // `align`: the largest power of two (<= 32) dividing every tensor base address involved.
 // A plane is vector-accessible when the base is aligned and its byte size is a multiple of the
 // vector width (then every plane start is aligned too).
-inline Plan make_plan(int N, int C, int64_t M, int dtype, int align, int sms) {
+inline Plan make_plan(int N, int C, int64_t M, int dtype, int align, int sms, int oversub = 1) {
     Plan p;
+    p.resident = 0;
     const int es = elem_size(dtype);
     if (align >= 32 && (M * es) % 32 == 0) p.vec = 32 / es;
     else if (align >= 16 && (M * es) % 16 == 0) p.vec = 16 / es;
@@ -60,6 +62,16 @@ inline Plan make_plan(int N, int C, int64_t M, int dtype, int align, int sms) {
         p.slots = 1;
     } else {
         p.group = 256;
+        // oversub > 1 (backward): cut the tensor into `oversub` slices per resident CTA, never smaller than 16 rounds of the
+        // CTA's loads (64 KB per tensor), never more than kMaxGrid (what the workspace's partial slots are sized for)
+        if (oversub > 1) {
+            p.resident = (int)max_ctas;
+            int64_t v = max_ctas * oversub;
+            if (v > kMaxGrid) v = kMaxGrid;
+            const int64_t min_per = 16 * kThreadsPerBlock;
+            if (p.total / v < min_per) v = p.total / min_per;
+            if (v > max_ctas) max_ctas = v; else p.resident = 0;
+        }
         int64_t per = ceil_div(p.total, max_ctas);
         per = ceil_div(per, kThreadsPerBlock) * kThreadsPerBlock;      // whole rows of threads
         p.per = per;
@@ -132,18 +144,59 @@ struct FusedPlan {
 // vector loads a thread keeps in flight for one tensor (same rule as the streaming kernels)
 inline int vpt_one_tensor(int vec) { const int v = 32 / vec; return v < 1 ? 1 : (v > 4 ? 4 : v); }
 
-// development knobs: MAXSTYLE_FUSED_PIECE_KB / MAXSTYLE_FUSED_WINDOW_MB override the two sizes above
+// Development knobs.  Every environment variable the library looks at is read ONCE, here, the first time any planner asks
+// (function-local static: initialised under the C++11 guard, immutable afterwards) -- no other getenv in the library, no
+// per-call reads, nothing that can change between two launches of a captured graph.  Unset or non-positive = the default.
 inline int64_t env_or(const char* name, int64_t dflt, int64_t unit) {
     const char* e = getenv(name);
     if (!e || !*e) return dflt;
     const long v = atol(e);
     return v > 0 ? (int64_t)v * unit : dflt;
 }
+inline int64_t env_flag(const char* name, int64_t dflt) {         // 0 is a meaningful value here
+    const char* e = getenv(name);
+    return (!e || !*e) ? dflt : (int64_t)atol(e);
+}
+
+constexpr int64_t kPairPieceBytesDefault = 112 * 1024;
+constexpr int kClusterMaxStagesDefault = 6;
+
+struct Tunables {
+    int64_t fused_piece_bytes, fused_window_bytes, fused_chunk, fused_keep_bytes;      // MAXSTYLE_FUSED_{PIECE_KB,WINDOW_MB,CHUNK,KEEP_MB}
+    int64_t ring_piece_chunks, ring_stages, ring_prefer;                               // MAXSTYLE_RING_{PIECE_CHUNKS,STAGES}, MAXSTYLE_RING
+    int64_t cluster_enabled, cluster_cs, cluster_stages, cluster_pieces;               // MAXSTYLE_CLUSTER, _CS, _STAGES, _PIECES
+    int64_t pair_enabled, pair_minb, pair_order, pair_piece_bytes;                     // MAXSTYLE_PAIR, _MINB, _ORDER, _PIECE_KB
+    int64_t bwd_oversub;                                                               // MAXSTYLE_BWD_OVERSUB: slices per resident CTA in the backward
+    int64_t pair_stagger_ns;                                                           // MAXSTYLE_PAIR_STAGGER_NS (-1: off)
+};
+
+inline const Tunables& tunables() {
+    static const Tunables t = [] {
+        Tunables v{};
+        v.fused_piece_bytes = env_or("MAXSTYLE_FUSED_PIECE_KB", kFusedPieceBytes, 1024);
+        v.fused_window_bytes = env_or("MAXSTYLE_FUSED_WINDOW_MB", kFusedWindowBytes, 1 << 20);
+        v.fused_chunk = env_or("MAXSTYLE_FUSED_CHUNK", 1, 1);
+        v.fused_keep_bytes = env_or("MAXSTYLE_FUSED_KEEP_MB", 0, 1 << 20);
+        v.ring_piece_chunks = env_or("MAXSTYLE_RING_PIECE_CHUNKS", 8, 1);
+        v.ring_stages = env_or("MAXSTYLE_RING_STAGES", 4, 1);
+        v.ring_prefer = env_or("MAXSTYLE_RING", 0, 1);
+        v.cluster_enabled = env_flag("MAXSTYLE_CLUSTER", 1);
+        v.cluster_cs = env_or("MAXSTYLE_CLUSTER_CS", 0, 1);
+        v.cluster_stages = env_or("MAXSTYLE_CLUSTER_STAGES", kClusterMaxStagesDefault, 1);
+        v.cluster_pieces = env_or("MAXSTYLE_CLUSTER_PIECES", 0, 1);
+        v.pair_enabled = env_flag("MAXSTYLE_PAIR", 1);
+        v.pair_minb = env_or("MAXSTYLE_PAIR_MINB", 4, 1);          // CTAs per SM the register budget is set for (3: 85 registers, 4: 64)
+        v.pair_order = env_or("MAXSTYLE_PAIR_ORDER", 0, 1);
+        v.pair_piece_bytes = env_or("MAXSTYLE_PAIR_PIECE_KB", kPairPieceBytesDefault, 1024);
+        v.pair_stagger_ns = env_flag("MAXSTYLE_PAIR_STAGGER_NS", 0);
+        v.bwd_oversub = env_or("MAXSTYLE_BWD_OVERSUB", 4, 1);          // measured 1: 135.4, 2: 140.0, 3: 135.9, 4: 133.4, 6: 133.0 us (config 1)
+        return v;
+    }();
+    return t;
+}
 
 inline FusedPlan make_fused_plan(int N, int C, int64_t M, int dtype, int align) {
-    static const int64_t piece_bytes = env_or("MAXSTYLE_FUSED_PIECE_KB", kFusedPieceBytes, 1024);
-    static const int64_t window_bytes = env_or("MAXSTYLE_FUSED_WINDOW_MB", kFusedWindowBytes, 1 << 20);
-    static const int64_t chunk = env_or("MAXSTYLE_FUSED_CHUNK", 1, 1);
+    const int64_t piece_bytes = tunables().fused_piece_bytes, window_bytes = tunables().fused_window_bytes, chunk = tunables().fused_chunk;
     FusedPlan f{};
     const int es = elem_size(dtype);
     if (align >= 32 && (M * es) % 32 == 0) f.vec = 32 / es;
@@ -183,9 +236,7 @@ struct RingPlan {
 };
 
 inline RingPlan make_ring_plan(int N, int C, int64_t M, int dtype, int align) {
-    static const int64_t piece_chunks = env_or("MAXSTYLE_RING_PIECE_CHUNKS", 8, 1);
-    static const int64_t stages = env_or("MAXSTYLE_RING_STAGES", 4, 1);
-    static const int64_t window_bytes = env_or("MAXSTYLE_FUSED_WINDOW_MB", kFusedWindowBytes, 1 << 20);
+    const int64_t piece_chunks = tunables().ring_piece_chunks, stages = tunables().ring_stages, window_bytes = tunables().fused_window_bytes;
     RingPlan r{};
     const int64_t pb = M * elem_size(dtype);
     const int64_t channel_bytes = (int64_t)N * pb;
@@ -205,7 +256,7 @@ inline RingPlan make_ring_plan(int N, int C, int64_t M, int dtype, int align) {
     // Measured equal to the register-staged window kernel within 2 % (profiles/r01_ring_knobs.txt: 110.7 vs 113.3 us on
     // the config-1 shape with 8-chunk pieces): the window kernel stays the default, MAXSTYLE_RING=1 or
     // MAXSTYLE_SWEEP_FORCE_RING select this one.
-    static const int64_t prefer = env_or("MAXSTYLE_RING", 0, 1);
+    const int64_t prefer = tunables().ring_prefer;
     r.profitable = prefer > 0 && pb >= kFusedProfitPlaneBytes && channel_bytes <= kFusedProfitChannelBytes;
     r.ok = true;
     return r;
@@ -250,7 +301,7 @@ inline ResidentPlan make_resident_plan(int N, int C, int64_t M, int dtype, int a
 
 // ---- cluster-resident forward (cluster_fwd.cuh): a plane split over a thread-block cluster, S stages per CTA ----
 constexpr int kClusterCtrlBytes = 16384;                     // == kClCtrlBytes
-constexpr int kClusterMaxStages = 6;                         // == kClMaxStages
+constexpr int kClusterMaxStages = kClusterMaxStagesDefault;                        // == kClMaxStages
 constexpr int kClusterMaxChunks = 16;                        // == kClMaxChunks
 constexpr int kClusterChunkUnit = 8192;                      // apply warps: 256 threads x 16 B x 2 in flight
 constexpr int kClusterMinPlaneBytes = 16 * 1024;
@@ -304,7 +355,7 @@ inline int cluster_max_pieces(int64_t M, int dtype) {
 
 // ---- paired forward (pair_fwd.cuh): a CTA owns a piece of a plane for both of its passes ----------------------
 constexpr int kPairMaxPieces = 32;
-constexpr int64_t kPairPieceBytes = 112 * 1024;              // largest piece: 592 CTAs x 112 KB live in L2 between the passes
+constexpr int64_t kPairPieceBytes = kPairPieceBytesDefault;             // largest piece: 592 CTAs x 112 KB live in L2 between the passes
 constexpr int64_t kPairMinPlaneBytes = 8 * 1024;
 
 struct PairPlan {
@@ -312,8 +363,8 @@ struct PairPlan {
     int vec, vpt, nvec, pieces, piece_vecs;
 };
 
-inline PairPlan make_pair_plan(int64_t M, int dtype, int align, int force_pieces = 0) {
-    static const int64_t piece_bytes = env_or("MAXSTYLE_PAIR_PIECE_KB", kPairPieceBytes, 1024);
+inline PairPlan make_pair_plan(int64_t M, int dtype, int align, int force_pieces = 0, int64_t planes = 0) {
+    const int64_t piece_bytes = tunables().pair_piece_bytes;
     PairPlan p{};
     const int es = elem_size(dtype);
     if (align >= 32 && (M * es) % 32 == 0) p.vec = 32 / es;
@@ -324,6 +375,9 @@ inline PairPlan make_pair_plan(int64_t M, int dtype, int align, int force_pieces
     p.nvec = (int)nvec;
     p.vpt = vpt_one_tensor(p.vec);
     int64_t P = force_pieces;
+    // A tensor that all but fits in L2 anyway needs no pieces: whole planes (fewer items, no sibling exchange) measured 10-17 %
+    // faster on 47-75 MB tensors of 147-196 KB planes (profiles/r02_fwd_paths.txt: 32x16x192x192, 20x16x224x224).
+    if (P <= 0 && planes > 0 && planes * pb <= (96ll << 20) && pb <= (256ll << 10)) P = 1;
     if (P <= 0) {
         // A piece of `len` vectors costs, per pass, len / round full rounds (256 threads x vpt loads in flight each) plus one
         // trip per 256 vectors of its ragged end, and ~1.5 rounds of publish / partner gap; 592 pieces must stay in L2 between
@@ -387,7 +441,7 @@ inline Workspace workspace_layout(int N, int C, int64_t M, int dtype, int layout
         const RingPlan rp = make_ring_plan(N, C, M, dtype, 16);
         if (rp.ok && (int64_t)C * rp.items_per_channel > items) items = (int64_t)C * rp.items_per_channel;
     }
-    w.res_error = off; off += 256;                           // int error @0, u64 queue @8, u32 done @16, u32 cluster launch counter @24
+    w.res_error = off; off += 256;                           // int error @0, u64 queue @8, u32 done @16, u32 launch counter @24
     w.res_flags = off; off = align_up(off + (size_t)2 * C * sizeof(uint32_t), 256);
     w.res_partials = off; off = align_up(off + (size_t)items * 16, 256);
     w.plane_ready = off; off = align_up(off + (size_t)planes * sizeof(uint32_t), 256);

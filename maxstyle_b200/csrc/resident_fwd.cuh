@@ -48,6 +48,7 @@ struct ResidentArgs {
     int flags;
     float eps;
     int in_policy, io_policy;
+    int stagger_cycles, slot_div;                    // CTA b starts (b / slot_div) * stagger_cycles late (the CTAs of an SM out of phase)
     float *mu, *sig, *scale, *shift;                 // [N, C]
     const int64_t* perm;
     const float *lmda, *gamma_noise, *beta_noise;
@@ -137,6 +138,10 @@ fwd_resident_kernel(const T* __restrict__ x, T* __restrict__ y, ResidentArgs a) 
         // =============================== producer warp ===============================
         if (t == TC) {
             const uint64_t pol = make_policy(a.in_policy);
+            if (a.stagger_cycles > 0) {                        // before the first ticket: nothing waits on a sleeping CTA
+                const long long wait = (long long)(blockIdx.x / a.slot_div) * a.stagger_cycles, t0 = clock64();
+                while (clock64() - t0 < wait) __nanosleep(200);
+            }
             for (int p = 0;; ++p) {
                 // The next ticket is taken only once chunk 0 of the current plane has been released, i.e. after the
                 // consumers are past their wait: a CTA never holds a ticket it cannot start loading at once (a ticket

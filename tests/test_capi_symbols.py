@@ -48,7 +48,7 @@ def test_host_entry_points(lib):
     assert b"workspace" in lib.maxstyle_strerror(3)
     n = lib.maxstyle_workspace_bytes(20, 64, 224, 224, 0, 0)
     assert n > 0 and n % 256 == 0
-    assert lib.maxstyle_workspace_bytes(20, 64, 224, 224, 0, 1) == 0 or True      # NHWC may be unimplemented
+    assert lib.maxstyle_workspace_bytes(20, 64, 224, 224, 0, 1) % 256 == 0 and lib.maxstyle_workspace_bytes(20, 64, 224, 224, 0, 1) > 0   # NHWC
     assert lib.maxstyle_workspace_bytes(0, 64, 224, 224, 0, 0) == 0               # bad shape
     assert lib.maxstyle_workspace_bytes(4, 4, 1, 1, 0, 0) == 0                    # M < 2: identity case upstream
     assert lib.maxstyle_workspace_bytes(4, 4, 8, 8, 7, 0) == 0                    # unknown dtype

@@ -171,7 +171,6 @@ def test_instance_stats_kernel_vs_oracle(shape):
     mu64, sig64 = O.instance_stats(x_np, 1e-6, dtype=np.float64)
     assert_rel(t2n(mu), mu64, 1e-6, "mu")
     assert np.abs(t2n(sig) / sig64 - 1).max() < 1e-5           # element-relative: sigma is never ~0 here
-    assert int(ws.count_nonzero()) == 0 or True                # partials may be non-zero; counters are checked below
     # the workspace counters are back to zero, so the same workspace serves the next call
     mu2, sig2 = F.instance_stats(x, 1e-6, ws)
     assert torch.equal(mu, mu2) and torch.equal(sig, sig2)     # and the result is run-to-run deterministic

@@ -1,0 +1,20 @@
+#!/bin/bash
+out=gpurun_out/${1:-held3}
+mkdir -p $out
+MAXSTYLE_PAIR_READ_CAP=50 timeout 900 python -m pytest tests/test_gpu_cluster_fwd.py tests/test_gpu_parity.py -q -x > $out/pytest.txt 2>&1; echo "pytest rc=$?"; tail -3 $out/pytest.txt
+S="20,64,224,224,f32"
+run() { echo "== $*" >> $out/held.txt; env "$@" python tools/cluster_bench.py --shapes "$S" --variants $V --iters 50 2>>$out/err.txt | cut -c1-330 >> $out/held.txt; }
+V=pair_p0,pair_p3 run X=0
+for c in 30 40 50 60 70 80; do V=pair_p0 run MAXSTYLE_PAIR_READ_CAP=$c; done
+V=pair_p0,pair_p3,pair_p4 run MAXSTYLE_PAIR_READ_CAP=50
+V=pair_p0 run MAXSTYLE_PAIR_READ_CAP=50 MAXSTYLE_PAIR_STAGGER_NS=3000
+V=pair_p0 run MAXSTYLE_PAIR_READ_CAP=60 MAXSTYLE_PAIR_STAGGER_NS=2000
+V=pair_p0 run MAXSTYLE_PAIR_STAGGER_NS=3000
+V=pair_p0 run MAXSTYLE_PAIR_READ_CAP=50 MAXSTYLE_PAIR_DEBUG=3
+V=pair_p0 run MAXSTYLE_PAIR_READ_CAP=50 MAXSTYLE_PAIR_DEBUG=4
+V=pair_p0,pair_p3 run MAXSTYLE_PAIR_READ_CAP=50 MAXSTYLE_PAIR_MINB=3
+S="64,32,512,512,f32;20,64,224,224,bf16;64,64,112,112,f32"
+V=pair_p0 run X=0
+V=pair_p0 run MAXSTYLE_PAIR_READ_CAP=50
+V=pair_p0 run MAXSTYLE_PAIR_STAGGER_NS=3000
+cat $out/held.txt
