@@ -377,7 +377,7 @@ inline PairPlan make_pair_plan(int64_t M, int dtype, int align, int force_pieces
     int64_t P = force_pieces;
     // A tensor that all but fits in L2 anyway needs no pieces: whole planes (fewer items, no sibling exchange) measured 10-17 %
     // faster on 47-75 MB tensors of 147-196 KB planes (profiles/r02_fwd_paths.txt: 32x16x192x192, 20x16x224x224).
-    if (P <= 0 && planes > 0 && planes * pb <= (96ll << 20) && pb <= (256ll << 10)) P = 1;
+    if (P <= 0 && planes >= 296 && planes * pb <= (96ll << 20) && pb <= (256ll << 10)) P = 1;      // and enough planes to fill the SMs
     if (P <= 0) {
         // A piece of `len` vectors costs, per pass, len / round full rounds (256 threads x vpt loads in flight each) plus one
         // trip per 256 vectors of its ragged end, and ~1.5 rounds of publish / partner gap; 592 pieces must stay in L2 between

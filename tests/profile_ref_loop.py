@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Where does the time of the reference's generate_max_style_image go with either layer?  (development tool; imports oracle/)
+"""Where does the time of the reference's generate_max_style_image go with either layer?  (measurement infrastructure under tests/: it imports oracle/)
 cProfile of the host side + torch.profiler totals of the device side, FCN_16 on the notebook batch."""
 import cProfile, io, os, pstats, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -40,7 +40,7 @@ def launches(src, out):
     mine_total = sum(sum(v) for v in mine.values())
     with open(out, "w") as f:
         f.write("ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised -> compare SHARES)\n")
-        f.write(f"command: python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline   (source: {src}/launches.csv)\n\n")
+        f.write(f"command: python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-parity   (source: {src}/launches.csv)\n\n")
         f.write(f"{'kernel':70s} {'n':>4s} {'mean_us':>10s} {'total_us':>10s} {'share_all':>9s} {'share_ours':>10s}\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             so = f"{100 * sum(v) / mine_total:9.1f}%" if k in mine else " " * 10
@@ -65,7 +65,7 @@ def to_bytes(val, unit):
 
 
 REPORTS = {   # capture -> the command it was taken from (tools/gpu_profile.sh)
-    "prof.ncu-rep": "python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline",
+    "prof.ncu-rep": "python bench.py --steps 3 --warmup 5 --no-e2e --no-cpu-baseline --no-parity   (-k regex:fwd_pair|bwd_nchw -s 12 -c 2)",
     "prof2.ncu-rep": "MAXSTYLE_SWEEP=18,3,4 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline   (two-pass forward forced)",
     "prof3.ncu-rep": "python tools/kernel_bench.py --fwd-only --dtype bf16 --sweeps 2,3,4 --iters 10   (bf16 config-1 shape)",
     "prof4.ncu-rep": "python tools/kernel_bench.py --layout nhwc --sweeps 2,2,4   (NHWC kernels)",
@@ -114,8 +114,9 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     launches(src, os.path.join(ROOT, "profiles", f"{name}_launches.txt"))
     ncu(src, os.path.join(ROOT, "profiles", f"{name}_ncu.txt"), os.path.join(ROOT, "profiles", "traffic.json"))
-    for extra in ("bench.json", "bench_ref.json", "pytest_gpu.txt", "smoke.txt", "fwd_paths.txt", "configs.jsonl", "sweep.jsonl",
-                  "loop_config2.txt", "ring_knobs.txt"):
+    for extra in ("bench.json", "bench_ref.json", "pytest_gpu.txt", "smoke.txt", "fwd_paths.txt", "fwd_paths.jsonl", "configs.jsonl", "sweep.jsonl",
+                  "loop_config2.txt", "loop_config2_ref.txt", "ring_knobs.txt", "bench_config3.json", "bench_config5.json", "ce2d.txt",
+                  "pm_series_bench.txt"):
         p = os.path.join(src, extra)
         if os.path.exists(p):
             with open(p) as fi, open(os.path.join(ROOT, "profiles", f"{name}_{extra}"), "w") as fo:
