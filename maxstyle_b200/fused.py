@@ -63,7 +63,7 @@ def rescale_intensity(y: torch.Tensor, minmax, new_min: float = 0.0, new_max: fl
     y = y.contiguous()
     n, c, h, w = y.shape
     out = torch.empty_like(y)
-    with torch.cuda.device(y.device):
+    with F.device_guard(y.device):
         rc = L.get_lib().maxstyle_rescale(y.data_ptr(), minmax[0].data_ptr(), minmax[1].data_ptr(), out.data_ptr(), float(new_min),
                                           float(new_max), float(eps), n, c, h, w, F.dtype_code(y), F._stream())
     L.check(rc, "maxstyle_rescale")

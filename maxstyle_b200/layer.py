@@ -242,7 +242,7 @@ class MaxStyle(nn.Module):
                                "on a B200 and has no CPU fallback")
         if self.gamma_noise.device != x.device:
             raise RuntimeError(f"maxstyle_b200: parameters are on {self.gamma_noise.device}, input on {x.device}")
-        with torch.cuda.device(x.device):
+        with F.device_guard(x.device):
             return F.MaxStyleFunction.apply(x, self.gamma_noise, self.beta_noise, self.lmda, self, L.PRE_NONE, 0.0, None)
 
     # ------------------------------------------------------------------------------------
@@ -275,6 +275,6 @@ class MaxStyle(nn.Module):
         if collect_minmax:
             minmax = (torch.full((n * c,), -1, dtype=torch.int32, device=z.device), torch.zeros(n * c, dtype=torch.int32, device=z.device))
         op = L.PRE_LEAKY_RELU if pre == "leaky_relu" else L.PRE_SIGMOID
-        with torch.cuda.device(z.device):
+        with F.device_guard(z.device):
             y = F.MaxStyleFunction.apply(z, self.gamma_noise, self.beta_noise, self.lmda, self, op, float(negative_slope), minmax)
         return (y, minmax) if collect_minmax else y

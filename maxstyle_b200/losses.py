@@ -76,7 +76,7 @@ class _CrossEntropy2D(torch.autograd.Function):
             out = []
             for t in ctx.grads:
                 if t is not None:
-                    with torch.cuda.device(t.device):
+                    with F.device_guard(t.device):
                         rc = lib.maxstyle_ce2d_scale(t.data_ptr(), g.data_ptr(), t.numel(), F.dtype_code(t), F._stream())
                     L.check(rc, "maxstyle_ce2d_scale")
                     F.launches.kernels += 1
@@ -89,7 +89,7 @@ class _CrossEntropy2D(torch.autograd.Function):
             return None, None, None, None, None, None
         n, c, h, w = logits.shape
         dlogits = torch.empty_like(logits)
-        with torch.cuda.device(logits.device):
+        with F.device_guard(logits.device):
             rc = lib.maxstyle_ce2d_bwd(logits.data_ptr(), target.data_ptr(), F._ptr(weight), F._ptr(mask), g.data_ptr(),
                                        dlogits.data_ptr(), n, c, h, w, F.dtype_code(logits), int(size_average), F._stream())
         L.check(rc, "maxstyle_ce2d_bwd")
@@ -135,5 +135,5 @@ def cross_entropy_2D(input, target, weight=None, size_average=True, mask=None, i
         mk = mask.detach().to(device=input.device, dtype=torch.float32).reshape(-1).contiguous()
         if mk.numel() != n * h * w:
             raise RuntimeError(f"maxstyle_b200: mask has {mk.numel()} entries, logits have {n * h * w} pixels")
-    with torch.cuda.device(input.device):
+    with F.device_guard(input.device):
         return _CrossEntropy2D.apply(logits, tgt, wt, mk, size_average, kind)

@@ -107,7 +107,7 @@ class MixStyle(nn.Module):
         if x.size(2) * x.size(3) < 2:
             raise RuntimeError("maxstyle_b200: MixStyle needs at least 2 elements per plane (unbiased variance)")
         lmda = lmda.to(device=x.device, dtype=torch.float32)
-        with torch.cuda.device(x.device):
+        with F.device_guard(x.device):
             if self.mix in ('random', 'crossdomain'):
                 if perm is None:
                     if self.mix == 'random':

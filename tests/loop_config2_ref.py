@@ -78,6 +78,37 @@ def device_busy_ms(ref, solver, image, label, cls, chans, n_iter, seed=7):
     return total / 1e3, layer / 1e3
 
 
+def splice_device_ms(ref, solver, image, chans, fused, reps=3):
+    """GPU busy time of ONE decoder pass with the three layers spliced (forward + backward of a scalar loss): the reference's
+    `MyDecoder.apply_max_style` with maxstyle_b200.MaxStyle layers, against `apply_max_style_fused` (LeakyReLU /
+    sigmoid applied by the layer's kernels as they load their input)."""
+    from maxstyle_b200 import MaxStyle, apply_max_style_fused
+    dec = solver.model["image_decoder"]
+    with torch.no_grad():
+        (z_i, _z_s), _ = solver.fast_predict(image)
+    torch.manual_seed(11)
+    layers = torch.nn.ModuleDict({str(i): MaxStyle(image.shape[0], chans[i], p=1.0) for i in (3, 4, 5)})
+
+    def once():
+        for m in layers.values():
+            m.zero_grad()
+        out = apply_max_style_fused(dec, z_i, layers, [3, 4, 5]) if fused else dec.apply_max_style(z_i, decoder_layers_indexes=[3, 4, 5], nn_style_augmentor_dict=layers)
+        out.square().mean().backward()
+
+    for _ in range(2):
+        once()
+    torch.cuda.synchronize()
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        for _ in range(reps):
+            once()
+        torch.cuda.synchronize()
+    tot = 0.0
+    for e in prof.key_averages():
+        t = getattr(e, "self_device_time_total", None)
+        tot += e.self_cuda_time_total if t is None else t
+    return tot / reps / 1e3
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
@@ -104,6 +135,11 @@ def main():
         k_our, kf_our, _, _ = timed_loop(ref, solver, image, label, MaxStyle, chans, args.n_iter, args.reps, keep_cache=True)
         d_ref, _ = device_busy_ms(ref, solver, image, label, ref.MaxStyle, chans, args.n_iter)
         d_our, d_layer = device_busy_ms(ref, solver, image, label, MaxStyle, chans, args.n_iter)
+        s_plain = splice_device_ms(ref, solver, image, chans, fused=False)
+        s_fused = splice_device_ms(ref, solver, image, chans, fused=True)
+        print(json.dumps({"config": "one decoder pass + backward, layers [3,4,5] spliced: " + name,
+                          "device_busy_ms_reference_splice_with_replacement_layers": round(s_plain, 3),
+                          "device_busy_ms_apply_max_style_fused": round(s_fused, 3), "speedup": round(s_plain / s_fused, 3)}), flush=True)
         print(json.dumps({
             "config": "BASELINE config 2 (reference solver, generate_max_style_image, layers [3,4,5], p=1, n_iter=%d): %s" % (args.n_iter, name),
             "layer_shapes": [[image.shape[0], chans[3], image.shape[2] // 2, image.shape[3] // 2], [image.shape[0], chans[4], image.shape[2], image.shape[3]],
