@@ -574,7 +574,8 @@ void launch_pair(const FwdCall& f, const PairArgs& a, int grid) {
 
 struct PairChoice { PairPlan plan; int grid; int use_order; };
 
-PairChoice choose_pair(int N, int C, int64_t M, int dtype, int align, int sms, int sweep, bool whole_channel, bool has_partner) {
+PairChoice choose_pair(int N, int C, int64_t M, int dtype, int align, int sms, int sweep, bool whole_channel, bool has_partner,
+                       int n_global) {
     PairChoice ch{};
     const int force_pieces = (sweep >> MAXSTYLE_SWEEP_CLUSTER_PIECES_SHIFT) & 63;
     ch.plan = make_pair_plan(M, dtype, align, force_pieces, (int64_t)N * C);
@@ -582,14 +583,17 @@ PairChoice choose_pair(int N, int C, int64_t M, int dtype, int align, int sms, i
     const int64_t minb = tunables().pair_minb;
     const int64_t items = (int64_t)N * C * ch.plan.pieces, cap = (int64_t)sms * (minb == 3 ? 3 : 4);
     ch.grid = (int)(items < cap ? items : cap);
-    // an item waits for items within W positions: grid > W keeps a CTA free for the lowest missing one
+    // An item waits for items within W positions: grid > W keeps a CTA free for the lowest missing one.  W = N * P when the
+    // whole channel is awaited (first forward) or the samples are taken in natural order; 2 * P when they are taken in cycle
+    // order of the global perm (pair_fwd.cuh) -- on one GPU and, in the steady state, across ranks.
+    const bool can_order = !whole_channel && N <= kPairMaxN && n_global <= kPairMaxNG && 2 * ch.plan.pieces < ch.grid;
     if ((int64_t)N * ch.plan.pieces >= ch.grid && (has_partner || whole_channel)) {
-        if (whole_channel || N > kPairMaxN || 2 * ch.plan.pieces >= ch.grid) { ch.plan.ok = false; return ch; }
+        if (!can_order) { ch.plan.ok = false; return ch; }
         ch.use_order = 1;
     }
     // experiment: walk the samples in cycle order whenever it is allowed (partner planes are then taken back to back)
     const int64_t force_order = tunables().pair_order;
-    if (force_order == 1 && !whole_channel && has_partner && N <= kPairMaxN && 2 * ch.plan.pieces < ch.grid) ch.use_order = 1;
+    if (force_order == 1 && has_partner && can_order) ch.use_order = 1;
     return ch;
 }
 
@@ -607,7 +611,8 @@ int try_pair_fwd(const FwdCall& f, const Workspace& w, int sms, int sweep) {
     if (f.N < 2) return -1;
     const bool multi = f.pt.world > 1, first = (f.flags & MAXSTYLE_COMPUTE_BATCH_STD) != 0;
     if (first && f.n_global > 32 * kPairStdRows) return -1;
-    const PairChoice ch = choose_pair(f.N, f.C, f.M, f.dtype, common_align(f.x, f.y), sms, sweep, first || multi, (f.flags & MAXSTYLE_MIX_STYLE) != 0);
+    const PairChoice ch = choose_pair(f.N, f.C, f.M, f.dtype, common_align(f.x, f.y), sms, sweep, first, (f.flags & MAXSTYLE_MIX_STYLE) != 0,
+                                      f.n_global);
     if (!ch.plan.ok || ch.plan.pieces > w.max_pieces) return -1;
     PairArgs a{};
     a.N = f.N; a.C = f.C; a.M = f.M;
@@ -899,7 +904,7 @@ int maxstyle_fwd_p2p(const void* x, void* y, float* mu_all, float* sig_all, int 
         return MAXSTYLE_ERR_BAD_ARG;
     if ((flags & MAXSTYLE_MIX_STYLE) && (!perm || !lmda)) return MAXSTYLE_ERR_BAD_ARG;
     if (!(flags & MAXSTYLE_NO_NOISE) && (!gamma_noise || !beta_noise)) return MAXSTYLE_ERR_BAD_ARG;
-    if (is_nhwc(layout, C) || N_global > kFusedMaxN) return MAXSTYLE_ERR_UNSUPPORTED;
+    if (is_nhwc(layout, C)) return MAXSTYLE_ERR_UNSUPPORTED;
     const int64_t M = (int64_t)H * W;
     const Workspace w = workspace_layout(N, C, M, dtype);
     if ((rc = check_workspace(workspace, workspace_bytes, w))) return rc;
@@ -915,6 +920,7 @@ int maxstyle_fwd_p2p(const void* x, void* y, float* mu_all, float* sig_all, int 
         rc = try_pair_fwd(f, w, sms, stats_sweep);
         if (rc >= 0) return rc;
     }
+    if (N_global > kFusedMaxN) return MAXSTYLE_ERR_UNSUPPORTED;        // the window / cluster kernels keep a channel's rows in shared memory
     if (!(stats_sweep & MAXSTYLE_SWEEP_NO_CLUSTER) && (stats_sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER)) {
         rc = try_cluster_fwd(f, w, sms, stats_sweep);
         if (rc >= 0) return rc;
@@ -1037,7 +1043,7 @@ int maxstyle_fwd_kernels(int N, int C, int H, int W, int dtype, int layout, int 
     auto pair_ok = [&]() {
         const int64_t pair_enabled = tunables().pair_enabled;
         if (N < 2 || (!(stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR) && pair_enabled != 1)) return false;
-        const PairChoice ch = choose_pair(N, C, M, dtype, 32, sm_count(), stats_sweep, false, true);
+        const PairChoice ch = choose_pair(N, C, M, dtype, 32, sm_count(), stats_sweep, false, true, N);
         return ch.plan.ok && ch.plan.pieces <= workspace_layout(N, C, M, dtype).max_pieces;
     };
     if ((stats_sweep & MAXSTYLE_SWEEP_FORCE_PAIR) && pair_ok()) return 1;
@@ -1078,7 +1084,7 @@ int maxstyle_fwd_geometry(int N, int C, int H, int W, int dtype, int stats_sweep
     const int64_t M = (int64_t)H * W;
     for (int i = 0; i < 12; ++i) out[i] = 0;
     if (!(stats_sweep & MAXSTYLE_SWEEP_FORCE_CLUSTER)) {
-        const PairChoice pc = choose_pair(N, C, M, dtype, 32, sms, stats_sweep, false, true);
+        const PairChoice pc = choose_pair(N, C, M, dtype, 32, sms, stats_sweep, false, true, N);
         if (!pc.plan.ok) return MAXSTYLE_ERR_UNSUPPORTED;
         out[2] = pc.grid; out[3] = pc.plan.piece_vecs * pc.plan.vec * elem_size(dtype); out[7] = sms; out[8] = pc.plan.pieces; out[9] = pc.use_order;
         out[10] = 1;

@@ -31,7 +31,8 @@
 
 namespace ms {
 
-constexpr int kPairMaxN = 1024;          // rows of the order table
+constexpr int kPairMaxN = 1024;          // rows of the order table (samples of this rank)
+constexpr int kPairMaxNG = 2048;         // samples of the global batch the cycle walk can hold
 constexpr int kPairStdRows = 16;         // first forward: rows of the channel a lane keeps in registers (n_global <= 512)
 constexpr long long kPairSpinLocal = 4000000000LL;      // ~2 s
 constexpr long long kPairSpinPeer = 40000000000LL;      // ~20 s: another rank may be late
@@ -87,8 +88,9 @@ struct PairShared {
     long long next_id;
     unsigned int tag, xtag;                  // this launch's tags (kept here, not in registers, across the streaming loops)
     float4 coef;                             // (mu, scale, shift) of the current item
-    unsigned short order[kPairMaxN];
-    int next_of[kPairMaxN];
+    unsigned short order[kPairMaxN];         // this rank's samples in cycle order of the GLOBAL perm
+    unsigned short next_g[kPairMaxNG];       // perm, staged for the walk
+    unsigned int seen[kPairMaxNG / 32];
 };
 
 // item id -> (channel, sample, piece); recomputed where needed instead of being kept in registers across the streaming loops
@@ -346,19 +348,22 @@ fwd_pair_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_constan
         const unsigned int xtag = a.pt.world > 1 ? *(volatile unsigned int*)a.epoch + 1u : wtag;
         const int lo = a.row_offset;
         if (a.use_order) {
-            for (int i = t; i < a.N; i += G) sh.next_of[i] = (int)a.perm[lo + i] - lo;
+            // Walk the cycles of the GLOBAL permutation and keep this rank's samples in the order they are met: a sample's partner
+            // is then the next sample of the walk (on this rank or on another one -- every rank walks the same cycles), or, for the
+            // sample that closes a cycle, one that came earlier.  Dependencies only point one step ahead in ONE order shared by
+            // all ranks, so the lowest unpublished plane of the whole job can always be taken by a free CTA of its rank.
+            const int NG = a.n_global;
+            for (int i = t; i < NG; i += G) sh.next_g[i] = (unsigned short)a.perm[i];
+            for (int i = t; i < kPairMaxNG / 32; i += G) sh.seen[i] = 0u;
             __syncthreads();
             if (t == 0) {
                 int k = 0;
-                unsigned int seen[kPairMaxN / 32];
-#pragma unroll
-                for (int w = 0; w < kPairMaxN / 32; ++w) seen[w] = 0u;
-                for (int s0 = 0; s0 < a.N; ++s0) {
-                    int n = s0;
-                    while (!((seen[n >> 5] >> (n & 31)) & 1u)) {
-                        seen[n >> 5] |= 1u << (n & 31);
-                        sh.order[k++] = (unsigned short)n;
-                        n = sh.next_of[n];
+                for (int s0 = 0; s0 < NG; ++s0) {
+                    int g = s0;
+                    while (!((sh.seen[g >> 5] >> (g & 31)) & 1u)) {
+                        sh.seen[g >> 5] |= 1u << (g & 31);
+                        if (g >= lo && g < lo + a.N) sh.order[k++] = (unsigned short)(g - lo);
+                        g = sh.next_g[g];
                     }
                 }
             }

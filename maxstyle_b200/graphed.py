@@ -140,8 +140,10 @@ class GraphedLayerStep:
                 ok = F.forward_p2p(self.peer, self.x, self.mu_all, self.sig_all, self.row_offset, self.perm, layer.lmda,
                                    layer.gamma_noise, layer.beta_noise, layer.gamma_std, layer.beta_std, flags, layer.eps, self.ws,
                                    self.scale, self.shift, self.y)
-                if self.one_kernel is None:
-                    self.one_kernel = ok                         # decided by the first call; the same on every rank
+                if self.one_kernel is None and not (flags & L.FLAG_COMPUTE_BATCH_STD):
+                    self.one_kernel = ok                         # decided by the first steady-state call (the first forward of a
+                                                                 # layer may be declined where the steady state is not); the
+                                                                 # answer depends on shapes only: the same on every rank
                 if ok:
                     return
             F.instance_stats(self.x, layer.eps, self.ws, self.mu_all, self.sig_all, self.row_offset)

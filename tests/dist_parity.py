@@ -187,6 +187,30 @@ def main():
         gsr.close()
         torch.cuda.synchronize()
         dist.barrier()
+    # ---- config-5 planes (512 x 512 = 1 MiB, 16 pieces each): a channel's N * P pieces exceed the grid, so the one-kernel forward
+    # takes the samples in cycle order of the GLOBAL permutation (pair_fwd.cuh) -- partners one step ahead, on whichever rank.
+    torch.manual_seed(seed + 1)
+    lay = GlobalBatchMaxStyle(40, 2, p=1.0)
+    genc = torch.Generator(device=dev).manual_seed(1900 + rank)
+    xr = torch.randn(40, 2, 512, 512, device=dev, generator=genc) * (1.0 + 0.2 * rank) - 0.1 * rank
+    dyr = torch.randn(40, 2, 512, 512, device=dev, generator=genc)
+    try:
+        gsr = GraphedLayerStep(lay, xr, dyr, exchange="p2p", one_kernel=True)
+    except RuntimeError as e:
+        if "peer-memory exchange requested but not available" not in str(e):
+            raise
+        gsr = None
+        errs["global_cycle_order"] = "symmetric memory unavailable on this system: skipped (every rank agrees)"
+    if gsr is not None:
+        assert gsr.one_kernel is True and gsr.kernels_per_step == 2, (gsr.one_kernel, gsr.kernels_per_step)
+        for _ in range(4):
+            gsr.run()
+        par = parity_check(lay, gsr, world, rank, dev, seed + 1)
+        assert par["ok"], f"rank {rank} global cycle order: {par}"
+        errs["global_cycle_order"] = {k: par[k] for k in ("y", "dx", "d_gamma", "d_beta", "d_lmda", "gamma_std", "beta_std")}
+        gsr.close()
+        torch.cuda.synchronize()
+        dist.barrier()
     print(f"[dist_parity] rank {rank}/{world} ok", json.dumps({k: (v if isinstance(v, (float, str)) else {a: f"{b:.1e}" for a, b in v.items()})
                                                                 for k, v in errs.items()}), flush=True)
     sys.stdout.flush()
