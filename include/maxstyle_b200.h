@@ -162,8 +162,8 @@ int maxstyle_tables(const float* mu_all, const float* sig_all, int table_ld, int
  * peer's buffer as 8-byte {value, epoch} words with single stores over NVLink (the epoch tag is the arrival flag: no
  * fence, no round trip), spins on the words of channel c in its own buffer and copies them into the table; `epoch` (device counter,
  * starts at 0, advanced by the kernel) numbers the exchanges so the call replays from a CUDA graph with fixed arguments;
- * `done` is a zeroed device word; `error` is set to 1 if a peer did not publish within ~2 s.  Every rank must make the same
- * sequence of calls. */
+ * `done` is a zeroed device word; if a peer does not publish within ~20 s `error` is set to 1 and the kernel traps (the launch
+ * fails).  Every rank must make the same sequence of calls. */
 size_t maxstyle_p2p_bytes(int N, int C, int world);
 int maxstyle_tables_p2p(const uint64_t* peers, int rank, int world, uint32_t* epoch, uint32_t* done, int* error,
                         float* mu_all, float* sig_all, int table_ld, int N_global, int row_offset, int N, int C,
@@ -176,13 +176,16 @@ int maxstyle_tables_p2p(const uint64_t* peers, int rank, int world, uint32_t* ep
 int maxstyle_rank_barrier(const uint64_t* peers, int rank, int world, int N, int C, uint32_t* bar_epoch, int* error,
                           maxstyle_stream_t stream);
 
-/* Multi-GPU whole forward in ONE kernel: the L2-window forward of maxstyle_fwd whose channel finaliser exchanges the channel's
- * (mu | sig) rows with the other ranks through the same peer-memory inboxes and epoch counter as maxstyle_tables_p2p (the
- * two calls may be mixed on one set of buffers as long as every rank makes the same sequence of calls).  x is read from HBM
- * once, y written once, and the exchange hides behind the 32 MB of streaming between a channel's statistics and its apply
- * items.  Returns MAXSTYLE_ERR_UNSUPPORTED without launching anything when the shape does not qualify for the window kernel
- * (the caller then runs maxstyle_stats -> maxstyle_tables_p2p -> maxstyle_apply); every rank sees the same answer for the
- * same shape.  A peer that does not publish within ~2 s raises the workspace error flag (maxstyle_workspace_status). */
+/* Multi-GPU whole forward in ONE kernel: the paired forward of maxstyle_fwd (every CTA owns a piece of a plane for both of its
+ * passes) whose piece-0 owners push their plane's (mu, sig) as 8-byte {value, tag} words into every peer's inbox -- the same
+ * peer-memory inboxes and epoch counter as maxstyle_tables_p2p (the two calls may be mixed on one set of buffers as long as
+ * every rank makes the same sequence of calls) -- and whose CTAs poll only their own inbox for the partner rows.  x is read from
+ * HBM once, y written once.  When a channel's pieces do not fit the grid the samples are taken in cycle order of the global
+ * permutation (N <= 1024 per rank, N_global <= 2048); the first forward of a layer (MAXSTYLE_COMPUTE_BATCH_STD) needs the whole
+ * channel in the grid.  With 2 ranks the L2-window forward is the second choice.  Returns MAXSTYLE_ERR_UNSUPPORTED without
+ * launching anything when the shape does not qualify (the caller then runs maxstyle_stats -> maxstyle_tables_p2p ->
+ * maxstyle_apply); every rank sees the same answer for the same shape and flags.  A peer that does not publish within ~20 s
+ * raises the workspace error flag and traps: the launch fails (maxstyle_workspace_status reads the flag). */
 int maxstyle_fwd_p2p(const void* x, void* y, float* mu_all, float* sig_all, int table_ld, int N_global, int row_offset,
                      const int64_t* perm, const float* lmda, const float* gamma_noise, const float* beta_noise,
                      float* gamma_std, float* beta_std, float* scale, float* shift,

@@ -10,19 +10,23 @@
 //     partner  fetch (mu, sig) of the partner plane (first forward: of the whole channel, and take the batch std); style_coeffs
 //     pass 2   stream the SAME piece again -- it was read microseconds ago and is still in L2 -- and write
 //              y = (x - mu) * A/sig + B                                                                           [L2 -> SM -> HBM]
-// 4 CTAs x 256 threads per SM run this loop out of phase, so while one CTA sits in its publish / partner gap (2-3 us of L2
-// round trips, warp 0 only) the other three stream; the pieces live in L2 only between their two passes (592 CTAs x <= 100 KB,
-// about what the L2 holds of such a stream: measured 16 % of the second reads miss at 59 MB, 68 % at 89 MB).  Compared with
-// fused_fwd.cuh (ordered statistics / apply queue with a 32 MB window): no control warp, no named-barrier hand-off per item, no
-// channel-wide finaliser on the steady-state path, and the re-read follows the first read by microseconds.
+// 4 CTAs x 256 threads per SM run this loop; while one CTA sits in its publish / partner gap (2-3 us of L2 round trips, warp 0
+// only) the other three stream.  The k-th CTA of an SM starts k * 3 us late: started together, all CTAs read for ~9 us and then
+// all sit in pass 2 (L2 hits in, L2 write-allocates out) with DRAM idle for ~10 us, and the rhythm persists (DRAM time series in
+// profiles/r02_pm_series.txt).  The pieces live in L2 only between their two passes (592 CTAs x <= 100 KB, about what the L2 holds
+// of such a stream: measured 15-24 % of the second reads miss at 59 MB, 68 % at 89 MB); the last batch of pass 1 does not even
+// leave the registers.  Compared with fused_fwd.cuh (ordered statistics / apply queue with a 32 MB window): no control warp, no
+// named-barrier hand-off per item, no channel-wide finaliser on the steady-state path.
 // Items are taken with an atomic ticket, in order (channel-major; the pieces of a plane adjacent).  An item publishes before
-// it waits, and waits only on publishes (its plane's pieces) or on the plane words of another plane, which that plane's
-// piece-0 owner publishes after waiting for nothing but publishes.  All of that lies within W positions of the item: W = N*P
-// (whole channel: first forward / multi GPU) or 2P when the samples are visited in cycle order of perm (the partner plane is
-// then the NEXT plane).  The ticket of the next item is taken only after the wait, so a CTA never parks a ticket behind a
-// wait; with more CTAs than W some CTA is always free to take the lowest missing item (host-side condition grid > W).
-// Variants tried and dropped: two items open per CTA, and a control warp resolving item k while seven
-// warps stream item k+1 -- both double the pieces alive in L2 and lost more to second-read misses than the hidden gap gave.
+// it waits, and waits only on publishes: its plane's pieces, and the plane words of its partner plane, which that plane's
+// piece-0 owner (on this rank or another) publishes after waiting for nothing but publishes.  In natural sample order all of that
+// lies within W = N*P positions (one channel); when a channel does not fit the grid the samples are taken in cycle order of the
+// GLOBAL perm, the same walk on every rank, so the partner is the NEXT plane of one order shared by all ranks (or an earlier
+// one, for the sample that closes a cycle): W = 2P.  The ticket of the next item is taken only after the wait, so a CTA never
+// parks a ticket behind a wait; with more CTAs than W the lowest unpublished plane of the whole job can always be taken by a
+// free CTA of its rank (host-side condition grid > W; the first forward awaits whole channels and needs N*P < grid).
+// Variants measured and dropped (profiles/r02_fwd_experiments.txt): two items open per CTA, a control warp
+// resolving item k while seven warps stream item k+1, partner statistics from piece words, bulk L2 prefetch, a read window.
 #pragma once
 #include "common.cuh"
 #include "kernels_nchw.cuh"
