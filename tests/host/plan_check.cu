@@ -14,13 +14,15 @@ using namespace ms;
 static int failures = 0;
 #define CHECK(cond, ...) do { if (!(cond)) { if (failures < 20) { printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } ++failures; } } while (0)
 
+// oversub > 1: the backward's plans -- more slices than resident CTAs, handed out by a ticket counter (slice index = partial slot)
 template <int G, int VPT>
-void check_case(int N, int C, int64_t M, int dtype, int align, int sms, int reverse) {
-    const Plan p = make_plan(N, C, M, dtype, align, sms);
+void check_case(int N, int C, int64_t M, int dtype, int align, int sms, int reverse, int oversub = 1) {
+    const Plan p = make_plan(N, C, M, dtype, align, sms, oversub);
     if (p.group != G) return;
     const Workspace w = workspace_layout(N, C, M, dtype);
-    CHECK(p.slots <= w.slots_bound, "slots %d > bound %d (N=%d C=%d M=%lld)", p.slots, w.slots_bound, N, C, (long long)M);
-    CHECK(p.grid >= 1 && p.grid <= sms * kBlocksPerSM, "grid %d", p.grid);
+    CHECK(p.slots <= w.slots_bound, "slots %d > bound %d (N=%d C=%d M=%lld oversub=%d)", p.slots, w.slots_bound, N, C, (long long)M, oversub);
+    CHECK(p.grid >= 1 && p.grid <= (oversub > 1 ? kMaxGrid : sms * kBlocksPerSM), "grid %d", p.grid);
+    if (oversub > 1 && p.resident > 0) CHECK(p.resident <= sms * kBlocksPerSM && p.grid > p.resident, "resident %d grid %d", p.resident, p.grid);
     Sweep g{};
     g.M = M; g.nvec = p.nvec; g.planes = p.planes; g.total = p.total; g.per = p.per; g.slots = p.slots; g.reverse = reverse;
     std::vector<int> cover((size_t)p.total, 0);
@@ -143,6 +145,12 @@ int main() {
                             if (vpt == 2) { check_case<256, 2>(s[0], s[1], M, dtype, align, sms, rev); check_case<32, 2>(s[0], s[1], M, dtype, align, sms, rev); }
                             if (vpt == 1) { check_case<256, 1>(s[0], s[1], M, dtype, align, sms, rev); check_case<32, 1>(s[0], s[1], M, dtype, align, sms, rev); }
                             ++cases;
+                            if (vpt == tensors_vpt2 && rev == 0) {                    // the backward: 2 tensors per thread, 4 slices per resident CTA
+                                if (vpt == 4) check_case<256, 4>(s[0], s[1], M, dtype, align, sms, rev, 4);
+                                if (vpt == 2) check_case<256, 2>(s[0], s[1], M, dtype, align, sms, rev, 4);
+                                if (vpt == 1) check_case<256, 1>(s[0], s[1], M, dtype, align, sms, rev, 4);
+                                ++cases;
+                            }
                         }
                     }
     const int nhwc_shapes[][4] = {{20, 64, 56, 56}, {4, 64, 48, 48}, {3, 16, 96, 96}, {2, 8, 64, 64}, {5, 256, 14, 14}, {3, 24, 40, 40},
