@@ -1,4 +1,6 @@
 #!/bin/bash
+# HISTORY (round 2): produced profiles/r02_fwd_experiments.txt.  The MAXSTYLE_PAIR_DEBUG / _READ_CAP / _STAGGER_GROUP knobs these runs
+# used were experiments and have been removed from the library again; MAXSTYLE_PAIR_STAGGER_NS / _MINB / _PIECE_KB / _ORDER remain.
 out=gpurun_out/${1:-held3}
 mkdir -p $out
 MAXSTYLE_PAIR_READ_CAP=50 timeout 900 python -m pytest tests/test_gpu_cluster_fwd.py tests/test_gpu_parity.py -q -x > $out/pytest.txt 2>&1; echo "pytest rc=$?"; tail -3 $out/pytest.txt

@@ -1,4 +1,6 @@
 #!/bin/bash
+# HISTORY (round 2): produced profiles/r02_fwd_experiments.txt.  The MAXSTYLE_PAIR_DEBUG / _READ_CAP / _STAGGER_GROUP knobs these runs
+# used were experiments and have been removed from the library again; MAXSTYLE_PAIR_STAGGER_NS / _MINB / _PIECE_KB / _ORDER remain.
 # experiment: do the CTAs of the paired forward run in lockstep?  start them out of phase / drop the waits (timing only)
 out=gpurun_out/${1:-stagger}
 mkdir -p $out
