@@ -99,7 +99,7 @@ struct PairShared {
 
 // item id -> (channel, sample, piece); recomputed where needed instead of being kept in registers across the streaming loops
 struct PairItem { int c, n, p; };
-__device__ __forceinline__ PairItem pair_item(const PairArgs& a, const unsigned short* order, long long id) {
+MS_HD PairItem pair_item(const PairArgs& a, const unsigned short* order, long long id) {
     PairItem it;
     const int per_channel = a.N * a.pieces;
     it.c = (int)(id / per_channel);
@@ -108,6 +108,23 @@ __device__ __forceinline__ PairItem pair_item(const PairArgs& a, const unsigned 
     it.p = r0 - k * a.pieces;
     it.n = a.use_order ? (int)order[k] : k;
     return it;
+}
+
+// This rank's samples [lo, lo + N) in the order the cycles of the GLOBAL permutation meet them (next_g = perm as 16-bit entries,
+// seen = a zeroed bitmap of NG bits).  A sample's partner perm[g] is the next sample of the walk, or -- for the sample that closes
+// a cycle, and for fixed points -- one met earlier; every rank walks the same cycles, so the positions agree across ranks.
+// Host-checked by tests/host/queue_check.cu.
+MS_HD int pair_cycle_order(const unsigned short* next_g, unsigned int* seen, int NG, int lo, int N, unsigned short* order) {
+    int k = 0;
+    for (int s0 = 0; s0 < NG; ++s0) {
+        int g = s0;
+        while (!((seen[g >> 5] >> (g & 31)) & 1u)) {
+            seen[g >> 5] |= 1u << (g & 31);
+            if (g >= lo && g < lo + N) order[k++] = (unsigned short)(g - lo);
+            g = next_g[g];
+        }
+    }
+    return k;
 }
 
 // Everything between the two passes of a piece, run by warp 0 and kept out of line (its register needs -- the rows of a channel
@@ -360,17 +377,7 @@ fwd_pair_kernel(const T* __restrict__ x, T* __restrict__ y, const __grid_constan
             for (int i = t; i < NG; i += G) sh.next_g[i] = (unsigned short)a.perm[i];
             for (int i = t; i < kPairMaxNG / 32; i += G) sh.seen[i] = 0u;
             __syncthreads();
-            if (t == 0) {
-                int k = 0;
-                for (int s0 = 0; s0 < NG; ++s0) {
-                    int g = s0;
-                    while (!((sh.seen[g >> 5] >> (g & 31)) & 1u)) {
-                        sh.seen[g >> 5] |= 1u << (g & 31);
-                        if (g >= lo && g < lo + a.N) sh.order[k++] = (unsigned short)(g - lo);
-                        g = sh.next_g[g];
-                    }
-                }
-            }
+            if (t == 0) pair_cycle_order(sh.next_g, sh.seen, NG, lo, a.N, sh.order);
         }
         if (t == 0) {
             if (a.stagger_cycles > 0) {                     // the ticket is taken after the delay: nothing waits on a sleeping CTA

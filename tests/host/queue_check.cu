@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../../maxstyle_b200/csrc/fused_fwd.cuh"
+#include "../../maxstyle_b200/csrc/pair_fwd.cuh"
 #include "../../maxstyle_b200/csrc/plan.h"
 
 using namespace ms;
@@ -49,6 +50,60 @@ static void check_queue(int N, int C, int pieces, int items_per_channel, int win
             if (s > last_ahead) last_ahead = s;
         }
         CHECK(last_ahead < first_apply, "%s: channel %d: window %d not respected", what, c, window);
+    }
+}
+
+// The paired forward's sample order (pair_cycle_order) and item map (pair_item):
+//  * every rank's order is a permutation of its samples and the sub-sequence of ONE global walk;
+//  * a sample's partner perm[g] sits at the next position of that walk, or at an earlier one (cycle closing / fixed point) --
+//    what bounds an item's wait to W = 2P tickets ahead on any rank;
+//  * item ids map onto (channel, sample, piece) one-to-one, channel-major, the pieces of a plane adjacent.
+static void check_pair_order(int world, int N, int P, int C, unsigned seed) {
+    const int NG = world * N;
+    std::vector<unsigned short> perm((size_t)NG);
+    for (int i = 0; i < NG; ++i) perm[i] = (unsigned short)i;
+    unsigned s = seed * 2654435761u + 12345u;
+    for (int i = NG - 1; i > 0; --i) { s = s * 1664525u + 1013904223u; const int j = (int)((s >> 8) % (unsigned)(i + 1)); std::swap(perm[i], perm[j]); }
+    std::vector<unsigned int> seen((size_t)(NG + 31) / 32, 0u);
+    std::vector<unsigned short> walk((size_t)NG);
+    CHECK(pair_cycle_order(perm.data(), seen.data(), NG, 0, NG, walk.data()) == NG, "global walk length");
+    std::vector<int> pos((size_t)NG, -1);
+    for (int k = 0; k < NG; ++k) { CHECK(pos[walk[k]] == -1, "sample twice in the walk"); pos[walk[k]] = k; }
+    for (int g = 0; g < NG; ++g) {
+        const int p = perm[g];
+        CHECK(pos[p] == pos[g] + 1 || pos[p] <= pos[g], "partner of %d at %d, own position %d (world %d N %d seed %u)", g, pos[p], pos[g], world, N, seed);
+    }
+    for (int r = 0; r < world; ++r) {
+        std::fill(seen.begin(), seen.end(), 0u);
+        std::vector<unsigned short> order((size_t)N);
+        CHECK(pair_cycle_order(perm.data(), seen.data(), NG, r * N, N, order.data()) == N, "rank order length");
+        int last = -1;
+        std::vector<int> hit((size_t)N, 0);
+        for (int k = 0; k < N; ++k) {
+            CHECK(order[k] < N, "order entry out of range");
+            if (order[k] >= N) continue;
+            hit[order[k]]++;
+            const int gp = pos[r * N + order[k]];
+            CHECK(gp > last, "rank %d order is not a sub-sequence of the global walk", r);
+            last = gp;
+        }
+        for (int n = 0; n < N; ++n) CHECK(hit[n] == 1, "rank %d sample %d appears %d times", r, n, hit[n]);
+        // item map with this order
+        PairArgs a{};
+        a.N = N; a.C = C; a.pieces = P; a.use_order = 1; a.total_items = (int64_t)N * C * P;
+        std::vector<int> cover((size_t)N * C * P, 0);
+        int64_t prev_plane = -1; int prev_p = -1;
+        for (int64_t id = 0; id < a.total_items; ++id) {
+            const PairItem it = pair_item(a, order.data(), id);
+            CHECK(it.c >= 0 && it.c < C && it.n >= 0 && it.n < N && it.p >= 0 && it.p < P, "pair_item out of range");
+            if (!(it.c >= 0 && it.c < C && it.n >= 0 && it.n < N && it.p >= 0 && it.p < P)) continue;
+            cover[((size_t)it.c * N + it.n) * P + it.p]++;
+            const int64_t plane = (int64_t)it.c * N + it.n;
+            if (it.p > 0) CHECK(plane == prev_plane && it.p == prev_p + 1, "pieces of a plane are not adjacent");
+            prev_plane = plane; prev_p = it.p;
+            CHECK(it.c == (int)(id / ((int64_t)N * P)), "items are not channel-major");
+        }
+        for (size_t i = 0; i < cover.size(); ++i) CHECK(cover[i] == 1, "item coverage %d", cover[i]);
     }
 }
 
@@ -94,6 +149,10 @@ int main() {
                     ++cases;
                 }
             }
+    const int orders[][4] = {{1, 20, 2, 3}, {1, 2, 1, 2}, {1, 3, 16, 2}, {2, 8, 2, 4}, {2, 40, 16, 2}, {4, 20, 2, 3}, {8, 20, 2, 2}, {8, 256, 16, 1}, {3, 7, 3, 2},
+                             {1, 1024, 2, 1}, {2, 1024, 1, 1}, {5, 33, 4, 2}};      // world, N per rank, pieces, channels
+    for (auto& o : orders)
+        for (unsigned seed = 1; seed <= 12; ++seed) { check_pair_order(o[0], o[1], o[2], o[3], seed); ++cases; }
     printf("%d cases, %d failures\n", cases, failures);
     return failures ? 1 : 0;
 }
